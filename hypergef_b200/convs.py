@@ -1,0 +1,85 @@
+"""hgsys conv layers and the 2-layer model the epoch-ms metric is quoted on.
+
+Signatures follow ``HyperGsys/model/ugsys/{hgnn,unigin,unigcnii}.py`` and
+``HyperGsys/model/gnn.py:110-134``; only the aggregation inside is new.
+"""
+from __future__ import annotations
+
+import math
+from types import SimpleNamespace
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .wrappers import HGNNAggr, UniGNNConv, UniGNNConvdeg
+
+__all__ = ["HyperGsysHGNN", "HyperGsysUinGINConv", "HyperGsysUniGCNIIConv", "HGsysHGNN"]
+
+
+class HyperGsysHGNN(nn.Module):
+    """model/ugsys/hgnn.py:7-27: ``Linear`` then the fused HGNN aggregation."""
+
+    def __init__(self, hyperg, in_channels, out_channels, first_aggr="sum", heads=1):
+        super().__init__()
+        self.W = nn.Linear(in_channels, heads * out_channels, bias=False)
+        self.Wdiag = torch.ones(hyperg.degE.shape[0], device=hyperg.device)
+        self.heads, self.in_channels, self.out_channels = heads, in_channels, out_channels
+        self.hyperg, self.degE, self.degV = hyperg, hyperg.degE, hyperg.degV
+        self.first_aggr = first_aggr
+
+    def forward(self, X):
+        X = self.W(X)
+        return HGNNAggr(self.hyperg, X, self.degE, self.degV, self.Wdiag, self.first_aggr)
+
+
+class HyperGsysUinGINConv(nn.Module):
+    """model/ugsys/unigin.py:7-26: ``(1+eps) XW + H H^T XW`` (reference spelling kept)."""
+
+    def __init__(self, hyperg, in_channels, out_channels, first_aggr="sum", heads=1):
+        super().__init__()
+        self.W = nn.Linear(in_channels, heads * out_channels, bias=False)
+        self.heads, self.in_channels, self.out_channels = heads, in_channels, out_channels
+        self.hyperg, self.degE, self.degV = hyperg, hyperg.degE, hyperg.degV
+        self.eps = nn.Parameter(torch.zeros(1))
+
+    def forward(self, X):
+        X = self.W(X)
+        return (1 + self.eps) * X + UniGNNConv(self.hyperg, X)
+
+
+class HyperGsysUniGCNIIConv(nn.Module):
+    """model/ugsys/unigcnii.py:7-26 with the ``alpha`` / ``beta`` it reads but never defines
+     passed at call time, as the pyg twin does (model/pygnn/unigcnii.py)."""
+
+    def __init__(self, hyperg, in_channels, out_channels, first_aggr="sum", heads=1):
+        super().__init__()
+        self.W = nn.Linear(in_channels, heads * out_channels, bias=False)
+        self.hyperg, self.degE, self.degV = hyperg, hyperg.degE, hyperg.degV
+
+    def forward(self, X, X0, alpha, beta):
+        Xv = UniGNNConvdeg(self.hyperg, X, self.degE, self.degV)
+        Xi = (1 - alpha) * Xv + alpha * X0
+        return (1 - beta) * Xi + beta * self.W(Xi)
+
+
+class HGsysHGNN(nn.Module):
+    """model/gnn.py:110-134: ``nlayer-1`` hidden convs + ``conv_out``, ReLU, dropouts, log-softmax."""
+
+    def __init__(self, args, hyperg, nfeat, nhid, nclass, nlayer=2, first_aggr="sum", nhead=1,
+                 conv=HyperGsysHGNN):
+        super().__init__()
+        args = args or SimpleNamespace(activation="relu", input_drop=0.6, dropout=0.6)
+        self.conv_out = conv(hyperg, nhid * nhead, nclass, first_aggr, nhead)
+        self.convs = nn.ModuleList(
+            [conv(hyperg, nfeat, nhid, first_aggr, nhead)] +
+            [conv(hyperg, nhid * nhead, nhid, first_aggr, nhead) for _ in range(nlayer - 2)])
+        self.act = {"relu": nn.ReLU(), "leaky_relu": nn.LeakyReLU()}[args.activation]
+        self.input_drop = nn.Dropout(args.input_drop)
+        self.dropout = nn.Dropout(args.dropout)
+
+    def forward(self, X):
+        X = self.input_drop(X)
+        for conv in self.convs:
+            X = self.dropout(self.act(conv(X)))
+        return F.log_softmax(self.conv_out(X), dim=1)

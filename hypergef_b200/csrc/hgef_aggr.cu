@@ -1,0 +1,375 @@
+// hgef_aggr.cu -- the fused two-stage aggregation for sm_100a.
+//
+//     Y = diag(a_out) . H . diag(s1*s2) . H^T . diag(a_in) . X
+//
+// One warp owns one balancer SEGMENT at a time (a slice of <= ngs members of one hyperedge):
+//   stage 1  gather the member rows of X with 128-bit read-only loads -- a feature row is
+//            contiguous, F/4 lanes cover it and 32/(F/4) rows are in flight per warp step --
+//            and reduce them in registers, finishing with a shuffle butterfly across the
+//            row groups: a warp-level segmented reduction, no atomics;
+//   scale    by s1[e]*s2[e] (degE, W);
+//   stage 2  scatter acc * a_out[v] to the same member rows of Y with 128-bit vector
+//            reductions (red.global.add.v4.f32, one L2 transaction per 16 B instead of
+//            the reference's four scalar atomics).
+// The hyperedge feature lives in registers only.  A hyperedge that the balancer cut into
+// w > 1 segments ("heavy") reduces its w partial sums into one L2-resident scratch row
+// and a second, small launch scatters the completed feature over the same segments, so
+// every member row is still gathered exactly once (the reference gathers it w times).
+//
+// The literal group schedule of the reference (hgnnaggr_cuda.cu:14-47) is kept as
+// hg_aggr_groups: same device code, one warp per balancer group.
+#include "hgef_plan.cuh"
+
+namespace hg {
+namespace {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kThreads = kWarpsPerBlock * 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+struct Args {
+  const int32_t *key, *colind, *seg_edge, *seg_slot, *seg_list;  // seg_list: optional indirection
+  const int32_t *row, *st, *ed;                                   // group schedule only
+  const float *X, *s1, *s2, *a_out, *a_in;
+  float *Y, *scratch;
+  int64_t nwork;   // segments (or listed segments, or groups)
+  int32_t F;
+  int32_t lpr;     // lanes per feature row (power of two <= 32); 32/lpr rows per warp step
+};
+
+__device__ __forceinline__ void red_add_v4(float *p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+__device__ __forceinline__ float edge_scale(const Args &a, int32_t e) {
+  float s = 1.0f;
+  if (a.s1) s = __ldg(a.s1 + e);
+  if (a.s2) s *= __ldg(a.s2 + e);
+  return s;
+}
+
+// ---- 128-bit path: F % 4 == 0.  Lane l holds columns (l % lpr)*4 + j*128 .. +3, j < VPL ----
+template <int VPL>
+struct Acc {
+  float4 v[VPL];
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+};
+
+// sum_{p in [lo,hi)} a_in[v_p] * X[v_p, cols]; every lane ends with the full sum of its columns
+template <int VPL>
+__device__ __forceinline__ void gather_rows(const Args &a, int32_t lo, int32_t hi, int lane, int col,
+                                            Acc<VPL> &acc) {
+  const int groups = 32 / a.lpr;
+  const int grp = lane / a.lpr;
+  const int F = a.F;
+  for (int32_t base = lo; base < hi; base += 32) {
+    const int n = min(32, hi - base);
+    int32_t my_v = 0;
+    float my_a = 1.0f;
+    if (lane < n) {
+      my_v = __ldg(a.colind + base + lane);
+      if (a.a_in) my_a = __ldg(a.a_in + my_v);
+    }
+#pragma unroll 4
+    for (int r0 = 0; r0 < n; r0 += groups) {
+      const int r = r0 + grp;
+      const int32_t v = __shfl_sync(kFull, my_v, r & 31);
+      const float w = __shfl_sync(kFull, my_a, r & 31);
+      if (r < n) {
+        const float *xp = a.X + (int64_t)v * F + col;
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+          if (col + j * 128 < F) {
+            const float4 x = __ldg(reinterpret_cast<const float4 *>(xp + j * 128));
+            acc.v[j].x = fmaf(w, x.x, acc.v[j].x);
+            acc.v[j].y = fmaf(w, x.y, acc.v[j].y);
+            acc.v[j].z = fmaf(w, x.z, acc.v[j].z);
+            acc.v[j].w = fmaf(w, x.w, acc.v[j].w);
+          }
+        }
+      }
+    }
+  }
+  // butterfly across the row groups (only when a row takes fewer than 32 lanes => VPL == 1)
+  for (int off = a.lpr; off < 32; off <<= 1) {
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      acc.v[j].x += __shfl_xor_sync(kFull, acc.v[j].x, off);
+      acc.v[j].y += __shfl_xor_sync(kFull, acc.v[j].y, off);
+      acc.v[j].z += __shfl_xor_sync(kFull, acc.v[j].z, off);
+      acc.v[j].w += __shfl_xor_sync(kFull, acc.v[j].w, off);
+    }
+  }
+}
+
+// Y[v_p, cols] += acc * a_out[v_p] for p in [lo,hi)
+template <int VPL>
+__device__ __forceinline__ void scatter_rows(const Args &a, int32_t lo, int32_t hi, int lane, int col,
+                                             const Acc<VPL> &acc) {
+  const int groups = 32 / a.lpr;
+  const int grp = lane / a.lpr;
+  const int F = a.F;
+  for (int32_t base = lo; base < hi; base += 32) {
+    const int n = min(32, hi - base);
+    int32_t my_v = 0;
+    float my_o = 1.0f;
+    if (lane < n) {
+      my_v = __ldg(a.colind + base + lane);
+      if (a.a_out) my_o = __ldg(a.a_out + my_v);
+    }
+#pragma unroll 4
+    for (int r0 = 0; r0 < n; r0 += groups) {
+      const int r = r0 + grp;
+      const int32_t v = __shfl_sync(kFull, my_v, r & 31);
+      const float o = __shfl_sync(kFull, my_o, r & 31);
+      if (r < n) {
+        float *yp = a.Y + (int64_t)v * F + col;
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+          if (col + j * 128 < F)
+            red_add_v4(yp + j * 128, make_float4(acc.v[j].x * o, acc.v[j].y * o, acc.v[j].z * o,
+                                                 acc.v[j].w * o));
+        }
+      }
+    }
+  }
+}
+
+template <int VPL>
+__device__ __forceinline__ void scale_acc(Acc<VPL> &acc, float s) {
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    acc.v[j].x *= s; acc.v[j].y *= s; acc.v[j].z *= s; acc.v[j].w *= s;
+  }
+}
+
+// Segment schedule, pass 1: all segments.  Light hyperedges finish here.
+template <int VPL>
+__global__ void __launch_bounds__(kThreads) seg_pass1_kernel(const Args a) {
+  const int lane = threadIdx.x & 31;
+  const int col = (lane & (a.lpr - 1)) * 4;
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+  for (int64_t s = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); s < a.nwork; s += nwarps) {
+    const int32_t lo = __ldg(a.key + s), hi = __ldg(a.key + s + 1);
+    const int32_t slot = __ldg(a.seg_slot + s);
+    Acc<VPL> acc;
+    acc.zero();
+    gather_rows<VPL>(a, lo, hi, lane, col, acc);
+    if (slot < 0) {
+      scale_acc<VPL>(acc, edge_scale(a, __ldg(a.seg_edge + s)));
+      scatter_rows<VPL>(a, lo, hi, lane, col, acc);
+    } else if (lane < a.lpr) {  // one row group publishes the partial sum
+      float *sp = a.scratch + (int64_t)slot * a.F + col;
+#pragma unroll
+      for (int j = 0; j < VPL; ++j)
+        if (col + j * 128 < a.F) red_add_v4(sp + j * 128, acc.v[j]);
+    }
+  }
+}
+
+// Segment schedule, pass 2: the segments of heavy hyperedges scatter the completed feature.
+template <int VPL>
+__global__ void __launch_bounds__(kThreads) seg_pass2_kernel(const Args a) {
+  const int lane = threadIdx.x & 31;
+  const int col = (lane & (a.lpr - 1)) * 4;
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+  for (int64_t i = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); i < a.nwork; i += nwarps) {
+    const int32_t s = __ldg(a.seg_list + i);
+    const int32_t lo = __ldg(a.key + s), hi = __ldg(a.key + s + 1);
+    const float *sp = a.scratch + (int64_t)__ldg(a.seg_slot + s) * a.F + col;
+    const float sc = edge_scale(a, __ldg(a.seg_edge + s));
+    Acc<VPL> acc;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      acc.v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      // plain (coherent) load: the scratch row was written by pass 1 of this call
+      if (col + j * 128 < a.F) acc.v[j] = *reinterpret_cast<const float4 *>(sp + j * 128);
+    }
+    scale_acc<VPL>(acc, sc);
+    scatter_rows<VPL>(a, lo, hi, lane, col, acc);
+  }
+}
+
+// Reference schedule: one warp per balancer group (read seg st[g], write seg ed[g]).
+template <int VPL>
+__global__ void __launch_bounds__(kThreads) group_kernel(const Args a) {
+  const int lane = threadIdx.x & 31;
+  const int col = (lane & (a.lpr - 1)) * 4;
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+  for (int64_t g = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); g < a.nwork; g += nwarps) {
+    const int32_t rs = __ldg(a.st + g), ws = __ldg(a.ed + g);
+    Acc<VPL> acc;
+    acc.zero();
+    gather_rows<VPL>(a, __ldg(a.key + rs), __ldg(a.key + rs + 1), lane, col, acc);
+    scale_acc<VPL>(acc, edge_scale(a, __ldg(a.row + g)));
+    scatter_rows<VPL>(a, __ldg(a.key + ws), __ldg(a.key + ws + 1), lane, col, acc);
+  }
+}
+
+// ---- scalar path: any F (lane l holds columns l, l+32, ...) -- scalar atomics like the
+// reference; used when F % 4 != 0 (e.g. the 7-class output layer) or pointers are unaligned.
+enum { kModeSeg1 = 0, kModeSeg2 = 1, kModeGroup = 2 };
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) scalar_kernel(const Args a) {
+  const int lane = threadIdx.x & 31;
+  const int F = a.F;
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+  for (int64_t i = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); i < a.nwork; i += nwarps) {
+    int32_t rlo, rhi, wlo, whi, e, slot = -1;
+    if (MODE == kModeGroup) {
+      const int32_t rs = a.st[i], ws = a.ed[i];
+      rlo = a.key[rs]; rhi = a.key[rs + 1]; wlo = a.key[ws]; whi = a.key[ws + 1]; e = a.row[i];
+    } else {
+      const int32_t s = MODE == kModeSeg2 ? a.seg_list[i] : (int32_t)i;
+      rlo = wlo = a.key[s]; rhi = whi = a.key[s + 1]; e = a.seg_edge[s]; slot = a.seg_slot[s];
+    }
+    const float sc = edge_scale(a, e);
+    for (int k = lane; k < F; k += 32) {
+      float acc = 0.f;
+      if (MODE == kModeSeg2) {
+        acc = a.scratch[(int64_t)slot * F + k];
+      } else {
+        for (int32_t p = rlo; p < rhi; ++p) {
+          const int32_t v = __ldg(a.colind + p);
+          const float x = __ldg(a.X + (int64_t)v * F + k);
+          acc = a.a_in ? fmaf(__ldg(a.a_in + v), x, acc) : acc + x;
+        }
+      }
+      if (MODE == kModeSeg1 && slot >= 0) {
+        atomicAdd(a.scratch + (int64_t)slot * F + k, acc);
+        continue;
+      }
+      acc *= sc;
+      for (int32_t p = wlo; p < whi; ++p) {
+        const int32_t v = __ldg(a.colind + p);
+        atomicAdd(a.Y + (int64_t)v * F + k, a.a_out ? acc * __ldg(a.a_out + v) : acc);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- host side
+inline int lanes_per_row(int F) {  // power of two >= min(F,128)/4
+  int need = (F < 128 ? F : 128) / 4, l = 1;
+  while (l < need) l <<= 1;
+  return l;
+}
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+inline unsigned grid_for(int64_t nwork, int sm_count, int blocks_per_sm) {
+  int64_t need = ceil_div<int64_t>(nwork, kWarpsPerBlock);
+  int64_t cap = (int64_t)sm_count * blocks_per_sm;
+  return (unsigned)(need < cap ? (need > 0 ? need : 1) : cap);
+}
+
+#define HG_DISPATCH_VPL(F, KERNEL, grid, stream, args)                        \
+  do {                                                                        \
+    if ((F) <= 128) KERNEL<1><<<grid, kThreads, 0, stream>>>(args);           \
+    else if ((F) <= 256) KERNEL<2><<<grid, kThreads, 0, stream>>>(args);      \
+    else KERNEL<4><<<grid, kThreads, 0, stream>>>(args);                      \
+  } while (0)
+
+int check_common(const float *X, float *Y, int32_t F) {
+  HG_REQUIRE(X != nullptr && Y != nullptr, "aggr: X or Y is NULL");
+  HG_REQUIRE(F >= 1, "aggr: feature length must be >= 1 (got %d)", F);
+  return HG_OK;
+}
+
+}  // namespace
+}  // namespace hg
+
+using namespace hg;
+
+extern "C" {
+
+int hg_aggr_groups(int64_t num_nodes, int64_t ngroup, const int32_t *d_key, const int32_t *d_row,
+                   const int32_t *d_st, const int32_t *d_ed, const int32_t *d_t_indices,
+                   const float *d_X, const float *d_s1, const float *d_s2, const float *d_a_out,
+                   const float *d_a_in, float *d_Y, int32_t F, int32_t flags, int device,
+                   void *stream) {
+  if (int rc = check_common(d_X, d_Y, F)) return rc;
+  HG_REQUIRE(num_nodes >= 0 && ngroup >= 0, "aggr_groups: negative size");
+  HG_REQUIRE(ngroup == 0 || (d_key && d_row && d_st && d_ed && d_t_indices),
+             "aggr_groups: a schedule array is NULL");
+  DeviceGuard guard(device);
+  HG_REQUIRE(guard.ok(), "aggr_groups: cannot select device %d", device);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!(flags & HG_ACCUMULATE))
+    HG_CUDA_TRY(cudaMemsetAsync(d_Y, 0, (size_t)num_nodes * F * sizeof(float), s));
+  if (ngroup == 0) return HG_OK;
+  int sm = 148;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+  Args a{};
+  a.key = d_key; a.colind = d_t_indices; a.row = d_row; a.st = d_st; a.ed = d_ed;
+  a.X = d_X; a.s1 = d_s1; a.s2 = d_s2; a.a_out = d_a_out; a.a_in = d_a_in; a.Y = d_Y;
+  a.nwork = ngroup; a.F = F; a.lpr = lanes_per_row(F);
+  const bool vec = F % 4 == 0 && F <= 512 && !(flags & HG_FORCE_SCALAR) && aligned16(d_X) && aligned16(d_Y);
+  const unsigned grid = grid_for(ngroup, sm, 8);
+  if (vec) HG_DISPATCH_VPL(F, group_kernel, grid, s, a);
+  else scalar_kernel<kModeGroup><<<grid, kThreads, 0, s>>>(a);
+  HG_CUDA_TRY(cudaGetLastError());
+  return HG_OK;
+}
+
+int hg_aggr_forward(hgPlan *plan, const float *d_X, const float *d_s1, const float *d_s2,
+                    const float *d_a_out, const float *d_a_in, float *d_Y, int32_t F, int32_t flags,
+                    void *stream) {
+  HG_REQUIRE(plan != nullptr, "aggr_forward: plan is NULL");
+  if (int rc = check_common(d_X, d_Y, F)) return rc;
+  if (!plan->canonical)
+    return hg_aggr_groups(plan->num_nodes, plan->ngroup, plan->key, plan->row, plan->st, plan->ed,
+                          plan->colind, d_X, d_s1, d_s2, d_a_out, d_a_in, d_Y, F, flags, plan->device,
+                          stream);
+  DeviceGuard guard(plan->device);
+  HG_REQUIRE(guard.ok(), "aggr_forward: cannot select device %d", plan->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!(flags & HG_ACCUMULATE))
+    HG_CUDA_TRY(cudaMemsetAsync(d_Y, 0, (size_t)plan->num_nodes * F * sizeof(float), s));
+  const bool heavy = plan->nheavy_segs > 0;
+  if (heavy) {
+    const size_t need = (size_t)plan->nheavy_edges * F;
+    if (need > plan->scratch_floats) {
+      HG_CUDA_TRY(cudaStreamSynchronize(s));
+      cudaFree(plan->scratch);
+      plan->scratch = nullptr;
+      plan->scratch_floats = 0;
+      if (cudaMalloc((void **)&plan->scratch, need * sizeof(float)) != cudaSuccess) {
+        cudaGetLastError();
+        return set_error(HG_ENOMEM, "aggr_forward: cannot allocate %zu bytes of scratch",
+                         need * sizeof(float));
+      }
+      plan->scratch_floats = need;
+    }
+    HG_CUDA_TRY(cudaMemsetAsync(plan->scratch, 0, need * sizeof(float), s));
+  }
+  Args a{};
+  a.key = plan->key; a.colind = plan->colind; a.seg_edge = plan->seg_edge; a.seg_slot = plan->seg_slot;
+  a.X = d_X; a.s1 = d_s1; a.s2 = d_s2; a.a_out = d_a_out; a.a_in = d_a_in; a.Y = d_Y;
+  a.scratch = plan->scratch; a.F = F; a.lpr = lanes_per_row(F);
+  const bool vec = F % 4 == 0 && F <= 512 && !(flags & HG_FORCE_SCALAR) && aligned16(d_X) && aligned16(d_Y);
+  a.nwork = plan->nseg;
+  unsigned grid = grid_for(plan->nseg, plan->sm_count, 8);
+  if (vec) HG_DISPATCH_VPL(F, seg_pass1_kernel, grid, s, a);
+  else scalar_kernel<kModeSeg1><<<grid, kThreads, 0, s>>>(a);
+  HG_CUDA_TRY(cudaGetLastError());
+  if (heavy) {
+    a.nwork = plan->nheavy_segs;
+    a.seg_list = plan->heavy_segs;
+    grid = grid_for(plan->nheavy_segs, plan->sm_count, 8);
+    if (vec) HG_DISPATCH_VPL(F, seg_pass2_kernel, grid, s, a);
+    else scalar_kernel<kModeSeg2><<<grid, kThreads, 0, s>>>(a);
+    HG_CUDA_TRY(cudaGetLastError());
+  }
+  return HG_OK;
+}
+
+}  // extern "C"

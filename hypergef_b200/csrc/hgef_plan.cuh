@@ -1,0 +1,23 @@
+// hgef_plan.cuh -- the aggregation plan (internal layout; opaque in the C-ABI).
+#pragma once
+
+#include "hgef_common.cuh"
+
+struct hgPlan {
+  int device = 0;
+  int64_t num_nodes = 0, num_edges = 0, nnz = 0, nseg = 0, ngroup = 0;
+  // borrowed from the caller (the balancer output and the CSR column indices of H^T)
+  const int32_t *key = nullptr, *row = nullptr, *st = nullptr, *ed = nullptr, *colind = nullptr;
+  // derived, owned
+  int32_t *seg_edge = nullptr;    // [nseg]   hyperedge of each segment
+  int32_t *seg_slot = nullptr;    // [nseg]   -1: the segment is its whole hyperedge ("light");
+                                  //          else row of `scratch` its hyperedge reduces into
+  int32_t *heavy_segs = nullptr;  // [nheavy_segs] the segments with slot >= 0, ascending
+  int64_t nheavy_edges = 0, nheavy_segs = 0;
+  int32_t canonical = 0;          // groups == full cross product in balancer order
+  int32_t max_seg_len = 0;
+  // scratch: partial hyperedge features of heavy hyperedges, [nheavy_edges, F]; L2-resident
+  float *scratch = nullptr;
+  size_t scratch_floats = 0;
+  int sm_count = 148;
+};

@@ -1,0 +1,360 @@
+"""The autograd ops of the fused aggregation path, over the C-ABI.
+
+Mirrors the two torch extensions of the reference (argument order and meaning kept):
+
+* ``hgnnaggr(balan_key, balan_row, group_st, group_ed, csrptr_t, indices_t, node_feat, degE, degV, W)``
+  -- ``HyperGsys/source/hgnnaggr/hgnnaggr.cc:122-129`` (autograd ``:37-65``)
+* ``hgnnaggr_mean / hgnnaggr_max(csrptr_t, indices_t, node_feat, degE, degV, W)`` -- ``:131-144``
+* ``unignnaggrdeg(key, row, st, ed, csrptr_t, indices_t, node_feat, degE, degV)`` and
+  ``unignnaggr(key, row, st, ed, csrptr_t, indices_t, node_feat)``
+  -- ``HyperGsys/source/unignnaggr/unignnaggr.cc:81-96``
+
+Differences, all deliberate:
+
+* backward is the TRUE transpose ``H S H^T diag(degV) dY`` by default; the reference re-runs
+  the forward on ``dY`` (``hgnnaggr.cc:58-60``), which is only the gradient when ``degV`` is
+  uniform.  ``set_backward_mode("reference")`` reproduces the reference.
+* ``W`` gets a gradient when it requires one (the reference returns none, ``hgnnaggr.cc:62-63``).
+* bad dtypes / devices / shapes raise ``TypeError`` / ``ValueError`` (the reference aborts
+  the process through C ``assert``, ``hgnnaggr_cuda.cu:8-12``).
+* any feature length works (the reference needs ``F < 32`` or ``F % 32 == 0``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from collections import OrderedDict
+
+import torch
+
+from . import _native
+
+__all__ = [
+    "hgnnaggr", "hgnnaggr_mean", "hgnnaggr_max", "unignnaggrdeg", "unignnaggr",
+    "set_backward_mode", "get_backward_mode", "aggregate", "aggregate_host", "Plan", "get_plan", "clear_plan_cache",
+    "launch_count",
+]
+
+_BACKWARD_MODE = "transpose"
+_LAUNCHES = 0           # C-ABI aggregation calls issued (bench.py reports it)
+
+
+def set_backward_mode(mode: str) -> None:
+    """``"transpose"`` (exact gradient, default) or ``"reference"`` (hgnnaggr.cc:58-60)."""
+    global _BACKWARD_MODE
+    if mode not in ("transpose", "reference"):
+        raise ValueError("backward mode must be 'transpose' or 'reference'")
+    _BACKWARD_MODE = mode
+
+
+def get_backward_mode() -> str:
+    return _BACKWARD_MODE
+
+
+def launch_count() -> int:
+    return _LAUNCHES
+
+
+# ----------------------------------------------------------------------------
+# argument checking
+# ----------------------------------------------------------------------------
+def _index(t, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (hypergef_b200 has no CPU path)")
+    if t.dtype == torch.int64:
+        t = t.to(torch.int32)
+    if t.dtype != torch.int32:
+        raise TypeError(f"{name} must be int32 (or int64), got {t.dtype}")
+    return t.contiguous().reshape(-1)
+
+
+def _feat(t, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (hypergef_b200 has no CPU path)")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    if t.dim() != 2:
+        raise ValueError(f"{name} must be [rows, F], got shape {tuple(t.shape)}")
+    return t.contiguous()
+
+
+def _scale(t, name, n, device):
+    """degE [M,1] / degV [N,1] / W [M]: read as flat float arrays (hgnnaggr_cuda.cu:29,43)."""
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    if t.device != device:
+        raise ValueError(f"{name} is on {t.device}, features are on {device}")
+    if t.numel() != n:
+        raise ValueError(f"{name} has {t.numel()} entries, expected {n}")
+    return t.detach().contiguous().reshape(-1)
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+# ----------------------------------------------------------------------------
+# plans
+# ----------------------------------------------------------------------------
+class Plan:
+    """Owns an ``hgPlan`` and keeps the borrowed index tensors alive."""
+
+    def __init__(self, key, row, st, ed, indices_t, num_nodes, num_edges):
+        self.tensors = (key, row, st, ed, indices_t)
+        self.device = key.device
+        self.num_nodes, self.num_edges = int(num_nodes), int(num_edges)
+        dev = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device_index = dev
+        handle = C.c_void_p()
+        _native.call("hg_plan_create", C.byref(handle), self.num_nodes, self.num_edges,
+                     indices_t.numel(), key.numel() - 1, row.numel(), key.data_ptr(), row.data_ptr(),
+                     st.data_ptr(), ed.data_ptr(), indices_t.data_ptr(), dev,
+                     torch.cuda.current_stream(dev).cuda_stream)
+        self.handle = handle
+        nseg, he, hs, canon = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int32()
+        _native.call("hg_plan_info", handle, C.byref(nseg), C.byref(he), C.byref(hs), C.byref(canon))
+        self.nseg, self.nheavy_edges, self.nheavy_segs = nseg.value, he.value, hs.value
+        self.canonical = bool(canon.value)
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            try:
+                _native.lib().hg_plan_destroy(h)
+            except Exception:
+                pass
+
+
+_PLANS: "OrderedDict[tuple, Plan]" = OrderedDict()
+_PLANS_LOCK = threading.Lock()
+_PLAN_CACHE_SIZE = 16
+
+
+def clear_plan_cache() -> None:
+    with _PLANS_LOCK:
+        _PLANS.clear()
+
+
+def get_plan(key, row, st, ed, indices_t, num_nodes, num_edges) -> Plan:
+    """Plan for this balancer output, cached on the identity of the five index tensors.
+
+    The cache entry holds the tensors, so a pointer cannot be recycled while its plan lives.
+    Index arrays are treated as immutable once used (as the reference's HyperGraph does).
+    """
+    key, row, st, ed, indices_t = (_index(t, n) for t, n in (
+        (key, "balan_key"), (row, "balan_row"), (st, "group_st"), (ed, "group_ed"),
+        (indices_t, "indices_t")))
+    if key.numel() < 2:
+        raise ValueError("balan_key needs at least one segment and the sentinel")
+    if not (row.numel() == st.numel() == ed.numel()):
+        raise ValueError("balan_row, group_st and group_ed must have the same length")
+    ident = (key.data_ptr(), row.data_ptr(), st.data_ptr(), ed.data_ptr(), indices_t.data_ptr(),
+             key.numel(), row.numel(), indices_t.numel(), int(num_nodes), int(num_edges), str(key.device))
+    with _PLANS_LOCK:
+        plan = _PLANS.get(ident)
+        if plan is not None:
+            _PLANS.move_to_end(ident)
+            return plan
+    plan = Plan(key, row, st, ed, indices_t, num_nodes, num_edges)
+    with _PLANS_LOCK:
+        _PLANS[ident] = plan
+        while len(_PLANS) > _PLAN_CACHE_SIZE:
+            _PLANS.popitem(last=False)
+    return plan
+
+
+def aggregate(plan: Plan, X, s1=None, s2=None, a_out=None, a_in=None, out=None, flags=0):
+    """``Y = diag(a_out) H diag(s1*s2) H^T diag(a_in) X`` -- one call of ``hg_aggr_forward``."""
+    global _LAUNCHES
+    X = _feat(X, "node_feat")
+    if X.device != plan.device:
+        raise ValueError(f"node_feat is on {X.device}, the graph is on {plan.device}")
+    N, M, F = plan.num_nodes, plan.num_edges, X.shape[1]
+    if X.shape[0] != N:
+        raise ValueError(f"node_feat has {X.shape[0]} rows, the graph has {N} vertices")
+    s1 = _scale(s1, "degE", M, X.device)
+    s2 = _scale(s2, "W", M, X.device)
+    a_out = _scale(a_out, "degV", N, X.device)
+    a_in = _scale(a_in, "degV", N, X.device)
+    if out is None:
+        out = torch.empty((N, F), dtype=torch.float32, device=X.device)
+    if F == 0 or N == 0:
+        return out.zero_() if not (flags & _native.HG_ACCUMULATE) else out
+    stream = torch.cuda.current_stream(plan.device_index).cuda_stream
+    _native.call("hg_aggr_forward", plan.handle, X.data_ptr(), _ptr(s1), _ptr(s2), _ptr(a_out),
+                 _ptr(a_in), out.data_ptr(), F, flags, stream)
+    _LAUNCHES += 1
+    return out
+
+
+def aggregate_host(plan: Plan, X_host, out_host=None, s1=None, s2=None, a_out=None, a_in=None):
+    """The same aggregation for HOST feature matrices (what a caller holding numpy / CPU torch
+    data uses): ``X_host`` [N,F] fp32 -> device, ``hg_aggr_forward``, result -> ``out_host``.
+    Pinned buffers make both copies asynchronous DMA; the graph and scales stay on the device."""
+    if not isinstance(X_host, torch.Tensor):
+        X_host = torch.as_tensor(X_host)
+    if X_host.is_cuda or X_host.dtype != torch.float32 or X_host.dim() != 2:
+        raise TypeError("aggregate_host needs a 2-D float32 CPU tensor")
+    X_host = X_host.contiguous()
+    if out_host is None:
+        out_host = torch.empty_like(X_host, pin_memory=X_host.is_pinned())
+    if out_host.shape != X_host.shape or out_host.dtype != torch.float32 or out_host.is_cuda \
+            or not out_host.is_contiguous():
+        raise ValueError("out_host must be a contiguous float32 CPU tensor of X_host's shape")
+    with torch.cuda.device(plan.device_index):
+        Xd = X_host.to(plan.device, non_blocking=True)
+        Yd = aggregate(plan, Xd, s1=s1, s2=s2, a_out=a_out, a_in=a_in)
+        out_host.copy_(Yd, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    return out_host
+
+
+def _weight_grad(csrptr_t, indices_t, X, G, s1, a_out, a_in, M):
+    dW = torch.empty(M, dtype=torch.float32, device=X.device)
+    dev = X.device.index if X.device.index is not None else torch.cuda.current_device()
+    _native.call("hg_weight_grad", M, csrptr_t.data_ptr(), indices_t.data_ptr(), X.data_ptr(),
+                 G.data_ptr(), _ptr(s1), _ptr(a_out), _ptr(a_in), dW.data_ptr(), X.shape[1], dev,
+                 torch.cuda.current_stream(dev).cuda_stream)
+    return dW
+
+
+# ----------------------------------------------------------------------------
+# autograd functions
+# ----------------------------------------------------------------------------
+class _FusedAggr(torch.autograd.Function):
+    """HGNNAggr / UniGNNAggrDeg / UniGNNAggr in one Function (scales optional)."""
+
+    @staticmethod
+    def forward(ctx, key, row, st, ed, csrptr_t, indices_t, node_feat, degE, degV, W, num_nodes):
+        node_feat = _feat(node_feat, "node_feat")
+        M = degE.numel() if degE is not None else (_index(csrptr_t, "csrptr_t").numel() - 1)
+        plan = get_plan(key, row, st, ed, indices_t, num_nodes, M)
+        out = aggregate(plan, node_feat, s1=degE, s2=W, a_out=degV)
+        ctx.plan, ctx.scales = plan, (degE, degV, W)
+        ctx.csr = (csrptr_t, indices_t)
+        ctx.w_needs_grad = W is not None and ctx.needs_input_grad[9]
+        if ctx.w_needs_grad:
+            ctx.save_for_backward(node_feat)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        degE, degV, W = ctx.scales
+        grad_out = grad_out.contiguous()
+        grad_x = grad_w = None
+        if ctx.needs_input_grad[6]:
+            if _BACKWARD_MODE == "reference":       # hgnnaggr.cc:58-60: forward applied to grad_out
+                grad_x = aggregate(ctx.plan, grad_out, s1=degE, s2=W, a_out=degV)
+            else:                                   # true transpose: degV moves to the gather side
+                grad_x = aggregate(ctx.plan, grad_out, s1=degE, s2=W, a_in=degV)
+        if ctx.w_needs_grad:
+            (x,) = ctx.saved_tensors
+            csrptr_t, indices_t = (_index(t, n) for t, n in zip(ctx.csr, ("csrptr_t", "indices_t")))
+            s1 = _scale(degE, "degE", ctx.plan.num_edges, x.device)
+            a_out = _scale(degV, "degV", ctx.plan.num_nodes, x.device)
+            grad_w = _weight_grad(csrptr_t, indices_t, x, grad_out, s1, a_out, None,
+                                  ctx.plan.num_edges).reshape(W.shape)
+        return (None,) * 6 + (grad_x, None, None, grad_w, None)
+
+
+def hgnnaggr(balan_key, balan_row, group_st, group_ed, csrptr_t, indices_t, node_feat, degE, degV, W):
+    """``Y = degV . H . (degE*W) . H^T . X`` (hgnnaggr.cc:122-129).  N is ``degV.size(0)``
+    as in the reference launcher (hgnnaggr_cuda.cu:366)."""
+    return _FusedAggr.apply(balan_key, balan_row, group_st, group_ed, csrptr_t, indices_t, node_feat,
+                            degE, degV, W, degV.shape[0])
+
+
+def unignnaggrdeg(balan_key, balan_row, group_st, group_ed, csrptr_t, indices_t, node_feat, degE, degV):
+    """``Y = degV . H . degE . H^T . X`` (unignnaggr.cc:81-88).  Uses ``degV[v]`` -- the
+    reference's non-smem kernels index degV by nnz position (unignnaggr_cuda.cu:41,212)."""
+    return _FusedAggr.apply(balan_key, balan_row, group_st, group_ed, csrptr_t, indices_t, node_feat,
+                            degE, degV, None, degV.shape[0])
+
+
+def unignnaggr(balan_key, balan_row, group_st, group_ed, csrptr_t, indices_t, node_feat):
+    """``Y = H . H^T . X`` (unignnaggr.cc:90-96).  N is ``in_feat.size(0)`` (unignnaggr_cuda.cu:460)."""
+    return _FusedAggr.apply(balan_key, balan_row, group_st, group_ed, csrptr_t, indices_t, node_feat,
+                            None, None, None, node_feat.shape[0])
+
+
+# ---- first-stage mean / max (hgnnaggr.cc:67-120) ----------------------------------------
+def _csr_args(csrptr_t, indices_t, node_feat, degE, degV, W):
+    csrptr_t, indices_t = _index(csrptr_t, "csrptr_t"), _index(indices_t, "indices_t")
+    X = _feat(node_feat, "node_feat")
+    M, N = csrptr_t.numel() - 1, X.shape[0]
+    if degV is not None and degV.numel() != N:
+        raise ValueError(f"degV has {degV.numel()} entries, node_feat has {N} rows")
+    return (csrptr_t, indices_t, X, _scale(degE, "degE", M, X.device), _scale(degV, "degV", N, X.device),
+            _scale(W, "W", M, X.device), N, M)
+
+
+def _dev_stream(t):
+    dev = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    return dev, torch.cuda.current_stream(dev).cuda_stream
+
+
+class _MeanF1(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, csrptr_t, indices_t, node_feat, degE, degV, W):
+        csrptr_t, indices_t, X, s1, a_out, s2, N, M = _csr_args(csrptr_t, indices_t, node_feat, degE, degV, W)
+        out = torch.empty_like(X)
+        dev, stream = _dev_stream(X)
+        _native.call("hg_aggr_mean", N, M, csrptr_t.data_ptr(), indices_t.data_ptr(), X.data_ptr(),
+                     _ptr(s1), _ptr(s2), _ptr(a_out), out.data_ptr(), X.shape[1], 0, dev, stream)
+        ctx.args = (csrptr_t, indices_t, s1, a_out, s2, N, M)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        # hgnnaggr_cuda.cu:115-142: the same mean operator applied to grad_out
+        csrptr_t, indices_t, s1, a_out, s2, N, M = ctx.args
+        G = grad_out.contiguous()
+        out = torch.empty_like(G)
+        dev, stream = _dev_stream(G)
+        _native.call("hg_aggr_mean", N, M, csrptr_t.data_ptr(), indices_t.data_ptr(), G.data_ptr(),
+                     _ptr(s1), _ptr(s2), _ptr(a_out), out.data_ptr(), G.shape[1], 0, dev, stream)
+        return None, None, out, None, None, None
+
+
+class _MaxF1(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, csrptr_t, indices_t, node_feat, degE, degV, W):
+        csrptr_t, indices_t, X, s1, a_out, s2, N, M = _csr_args(csrptr_t, indices_t, node_feat, degE, degV, W)
+        out = torch.empty_like(X)
+        record = torch.empty((M, X.shape[1]), dtype=torch.int32, device=X.device)
+        dev, stream = _dev_stream(X)
+        _native.call("hg_aggr_max_forward", N, M, csrptr_t.data_ptr(), indices_t.data_ptr(), X.data_ptr(),
+                     _ptr(s1), _ptr(s2), _ptr(a_out), out.data_ptr(), record.data_ptr(), X.shape[1], 0,
+                     dev, stream)
+        ctx.args = (csrptr_t, indices_t, s1, a_out, s2, N, M, record)
+        ctx.mark_non_differentiable(record)
+        return out, record
+
+    @staticmethod
+    def backward(ctx, grad_out, _grad_record):
+        csrptr_t, indices_t, s1, a_out, s2, N, M, record = ctx.args
+        G = grad_out.contiguous()
+        dX = torch.empty_like(G)
+        dev, stream = _dev_stream(G)
+        _native.call("hg_aggr_max_backward", N, M, csrptr_t.data_ptr(), indices_t.data_ptr(), G.data_ptr(),
+                     _ptr(s1), _ptr(s2), _ptr(a_out), record.data_ptr(), dX.data_ptr(), G.shape[1], 0,
+                     dev, stream)
+        return None, None, dX, None, None, None
+
+
+def hgnnaggr_mean(csrptr_t, indices_t, node_feat, degE, degV, W):
+    """First-stage MEAN (hgnnaggr.cc:131-136)."""
+    return _MeanF1.apply(csrptr_t, indices_t, node_feat, degE, degV, W)
+
+
+def hgnnaggr_max(csrptr_t, indices_t, node_feat, degE, degV, W):
+    """First-stage MAX; returns ``[out, record_table]`` (hgnnaggr.cc:138-144)."""
+    return list(_MaxF1.apply(csrptr_t, indices_t, node_feat, degE, degV, W))

@@ -1,0 +1,171 @@
+/*
+ * hgef_b200.h -- C-ABI of libhgef_b200.so: the B200-native (sm_100a) drop-in for
+ * HyperGef's fused hypergraph message-passing path.
+ *
+ * Plain pointers and sizes only (no torch types).  Every entry point names the
+ * reference interface it replaces (paths relative to fishmingyu/HyperGef).
+ * The reference binds this path through two pybind11 torch extensions
+ * (`hgnnaggr`, `unignnaggr`, setup.py:18); INTEGRATION.md shows the stub a
+ * maintainer would put in their place.
+ *
+ * Conventions
+ *   - all functions return 0 (HG_OK) or an HG_E* code; hg_last_error() gives the
+ *     thread-local message of the last failure on the calling thread.  The
+ *     reference aborts through C assert (hgnnaggr_cuda.cu:8-12) and never checks
+ *     a launch; here nothing aborts.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream,
+ *     which is what the reference always uses, hgnnaggr_cuda.cu:383).
+ *   - device pointers are prefixed d_, host pointers h_.  All index arrays are
+ *     int32 (the reference's `typedef int Index`, include/util/check.cuh:11);
+ *     addresses are formed in 64 bits (the reference overflows at N*F >= 2^31).
+ *   - feature matrices are fp32, row-major, contiguous [rows, F].
+ *   - entry points are re-entrant; an hgPlan is immutable after creation except
+ *     for its scratch buffer, so one plan must not run on two streams at once.
+ */
+#ifndef HGEF_B200_H_
+#define HGEF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HG_API __attribute__((visibility("default")))
+
+enum {
+  HG_OK = 0,
+  HG_EINVAL = 1,   /* bad argument (Python shim raises ValueError)            */
+  HG_ECUDA = 2,    /* CUDA runtime / launch failure (RuntimeError)            */
+  HG_ENOMEM = 3,   /* allocation failure (MemoryError)                        */
+  HG_EEMPTY = 4,   /* balancer on a matrix with no non-zero: the reference
+                      raises IndexError at balancer.py:32 (balan_key[-1])     */
+  HG_EGRAPH = 5    /* plan validation: index out of range in the graph/balancer
+                      arrays (the reference would read/write out of bounds)   */
+};
+
+HG_API const char *hg_last_error(void);
+HG_API int hg_abi_version(void);
+/* Compute capability of `device` as major*10+minor, or <0 on error. */
+HG_API int hg_device_cc(int device);
+
+/* ------------------------------------------------------------------------- *
+ * Balancer.  Replaces balance_schedule.balancer, HyperGsys/balancer.py:15-33
+ * (C++ twin hgnn_ef_full_balance_cpu, include/taskbalancer/balancer_kernel.cuh:229-259).
+ * Output is bit-identical to the reference: nkey = S+1 segment offsets (sentinel
+ * included), ngroup = sum_e w_e^2 groups in (row, write-segment, read-segment) order.
+ * count -> allocate -> fill.  HG_EEMPTY when no row has a non-zero.
+ * ------------------------------------------------------------------------- */
+HG_API int hg_balance_count_host(int64_t nrow, const int32_t *h_csrptr, int32_t ngs,
+                                 int64_t *nkey, int64_t *ngroup);
+HG_API int hg_balance_fill_host(int64_t nrow, const int32_t *h_csrptr, int32_t ngs,
+                                int32_t *h_key, int32_t *h_row, int32_t *h_st, int32_t *h_ed);
+/* Device twin (the reference left this as a TODO, source/balancer/balancer_kernel.cu:34).
+ * count synchronises `stream` once to return the two sizes. */
+HG_API int hg_balance_count_dev(int64_t nrow, const int32_t *d_csrptr, int32_t ngs,
+                                int64_t *nkey, int64_t *ngroup, int device, void *stream);
+HG_API int hg_balance_fill_dev(int64_t nrow, const int32_t *d_csrptr, int32_t ngs,
+                               int64_t nkey, int64_t ngroup, int32_t *d_key, int32_t *d_row,
+                               int32_t *d_st, int32_t *d_ed, int device, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * Incidence -> CSR of H and of H^T.  Replaces the scipy calls of
+ * HyperGraph.__init__, HyperGsys/hypergraph.py:23-25
+ *   H = coo_matrix((1,(V,E)),(N,M)).tocsr() ; H_T = H.transpose().tocsr()
+ * with scipy's semantics: column indices ascending in a row, duplicate pairs
+ * merged with summed value (data = multiplicity).  `nnz_out` <= nnz_in.
+ * Output arrays need room for nnz_in entries; indptr arrays nrow+1 / ncol+1.
+ * ------------------------------------------------------------------------- */
+HG_API int hg_csr_build_host(int64_t nrow, int64_t ncol, int64_t nnz_in, const int64_t *h_rows,
+                             const int64_t *h_cols, int32_t *h_indptr, int32_t *h_indices,
+                             float *h_data, int32_t *h_t_indptr, int32_t *h_t_indices,
+                             float *h_t_data, int64_t *nnz_out);
+HG_API int hg_csr_build_dev(int64_t nrow, int64_t ncol, int64_t nnz_in, const int64_t *d_rows,
+                            const int64_t *d_cols, int32_t *d_indptr, int32_t *d_indices,
+                            float *d_data, int32_t *d_t_indptr, int32_t *d_t_indices,
+                            float *d_t_data, int64_t *nnz_out, int device, void *stream);
+/* Degree scalings, hypergraph.py:34-45: out[r] = (sum of data in row r)^power, with
+ * +inf replaced by 1 when `inf_to_one` (degV: power -0.5, inf_to_one 1; degE: -1, 0). */
+HG_API int hg_degree_scale_dev(int64_t nrow, const int32_t *d_indptr, const float *d_data,
+                               float power, int inf_to_one, float *d_out, int device,
+                               void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * Aggregation plan: everything derived once from the balancer output so that the
+ * per-call path is a single fused launch.  Borrowed pointers (d_key .. d_t_indices)
+ * must outlive the plan.  Validates every index (HG_EGRAPH).
+ *   nseg   = nkey - 1 (segments), ngroup = len(group_row)
+ * ------------------------------------------------------------------------- */
+typedef struct hgPlan hgPlan;
+HG_API int hg_plan_create(hgPlan **plan, int64_t num_nodes, int64_t num_edges, int64_t nnz,
+                          int64_t nseg, int64_t ngroup, const int32_t *d_key,
+                          const int32_t *d_row, const int32_t *d_st, const int32_t *d_ed,
+                          const int32_t *d_t_indices, int device, void *stream);
+HG_API int hg_plan_destroy(hgPlan *plan);
+/* what the plan found: S, #heavy hyperedges (w_e > 1), #segments of heavy hyperedges,
+ * 1 when the groups are the balancer's canonical full cross product. */
+HG_API int hg_plan_info(const hgPlan *plan, int64_t *nseg, int64_t *nheavy_edges,
+                        int64_t *nheavy_segs, int32_t *canonical);
+
+/* flags for hg_aggr_* */
+enum {
+  HG_ACCUMULATE = 1,     /* do not zero-fill Y first (reference: torch::zeros, hgnnaggr_cuda.cu:374) */
+  HG_FORCE_SCALAR = 4    /* disable the 128-bit path (testing) */
+};
+
+/* ------------------------------------------------------------------------- *
+ * Fused two-stage aggregation
+ *     Y = diag(a_out) . H . diag(s1*s2) . H^T . diag(a_in) . X
+ * in one pass over the balancer segments; the hyperedge feature never goes to DRAM.
+ * Replaces hgnnaggr_fp_cuda (source/hgnnaggr/hgnnaggr_cuda.cu:350-406) with
+ * s1=degE, s2=W, a_out=degV; unignnaggrdeg_fp_cuda (source/unignnaggr/unignnaggr_cuda.cu:392-447)
+ * with s2=NULL; unignnaggr_fp_cuda (:449-488) with all scales NULL.  Any scale may
+ * be NULL (= 1).  a_in is the gather-side scale of the true-transpose backward
+ * (dX = H diag(s) H^T diag(degV) dY); the reference's own backward re-runs the
+ * forward on dY (hgnnaggr.cc:58-60), which is the same call as the forward.
+ * Any F >= 1 (the reference requires F < 32 or F % 32 == 0).
+ * ------------------------------------------------------------------------- */
+HG_API int hg_aggr_forward(hgPlan *plan, const float *d_X, const float *d_s1, const float *d_s2,
+                           const float *d_a_out, const float *d_a_in, float *d_Y, int32_t F,
+                           int32_t flags, void *stream);
+
+/* The reference's schedule, literally: one work unit per balancer GROUP (read segment
+ * group_st[g], scale row group_row[g], write segment group_ed[g]) exactly as
+ * HGNNAggr_forward_kernel (hgnnaggr_cuda.cu:14-47).  Needs no plan and accepts any
+ * group arrays; kept for parity tests and as the "reference schedule" ablation. */
+HG_API int hg_aggr_groups(int64_t num_nodes, int64_t ngroup, const int32_t *d_key,
+                          const int32_t *d_row, const int32_t *d_st, const int32_t *d_ed,
+                          const int32_t *d_t_indices, const float *d_X, const float *d_s1,
+                          const float *d_s2, const float *d_a_out, const float *d_a_in,
+                          float *d_Y, int32_t F, int32_t flags, int device, void *stream);
+
+/* f1-mean / f1-max first-stage variants over the un-balanced CSR of H^T.
+ * Replace hgnnaggr_mean_fp_cuda / _bp_cuda (hgnnaggr_cuda.cu:408-470) and
+ * hgnnaggr_max_fp_cuda / _bp_cuda (:472-543).  The hyperedge loop is bounded by
+ * num_edges (the reference bounds it by N).  d_record is int32 [M,F]. */
+HG_API int hg_aggr_mean(int64_t num_nodes, int64_t num_edges, const int32_t *d_t_indptr,
+                        const int32_t *d_t_indices, const float *d_X, const float *d_s1,
+                        const float *d_s2, const float *d_a_out, float *d_Y, int32_t F,
+                        int32_t flags, int device, void *stream);
+HG_API int hg_aggr_max_forward(int64_t num_nodes, int64_t num_edges, const int32_t *d_t_indptr,
+                               const int32_t *d_t_indices, const float *d_X, const float *d_s1,
+                               const float *d_s2, const float *d_a_out, float *d_Y,
+                               int32_t *d_record, int32_t F, int32_t flags, int device,
+                               void *stream);
+HG_API int hg_aggr_max_backward(int64_t num_nodes, int64_t num_edges, const int32_t *d_t_indptr,
+                                const int32_t *d_t_indices, const float *d_G, const float *d_s1,
+                                const float *d_s2, const float *d_a_out, const int32_t *d_record,
+                                float *d_dX, int32_t F, int32_t flags, int device, void *stream);
+
+/* Gradient of the hyperedge weight W (the reference op returns none, hgnnaggr.cc:62-63;
+ * un-scaled host reference include/util/check.cuh:116-143):
+ *   dW[e] = s1[e] * sum_k (sum_{u in e} a_in[u] X[u,k]) * (sum_{v in e} a_out[v] G[v,k]) */
+HG_API int hg_weight_grad(int64_t num_edges, const int32_t *d_t_indptr,
+                          const int32_t *d_t_indices, const float *d_X, const float *d_G,
+                          const float *d_s1, const float *d_a_out, const float *d_a_in,
+                          float *d_dW, int32_t F, int device, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HGEF_B200_H_ */

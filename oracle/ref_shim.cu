@@ -1,0 +1,89 @@
+// ref_shim.cu -- TEST/BASELINE INFRASTRUCTURE ONLY (never linked into the product).
+//
+// Thin extern "C" doors onto the UNMODIFIED reference sources, which are
+// #included from where they lie under /root/reference (see oracle/Makefile,
+// -I$(REF)/HyperGsys/include).  Nothing of the reference is copied into this
+// repository; the resulting library goes to oracle/_ref/ (git-ignored).
+//
+//   ref_balance_*      -> hgnn_ef_full_balance_cpu   include/taskbalancer/balancer_kernel.cuh:229-259
+//   ref_hyperaggr_host -> util::hyperaggr_reference_host   include/util/check.cuh:82-114
+//   ref_spmm_host      -> util::spmm_reference_host        include/util/check.cuh:60-79
+//   ref_weight_grad    -> util::hgnnbp_reference_host      include/util/check.cuh:116-143
+//   ref_lab_full_gpu   -> HyperGAggr_Edgefused_Balance_Full_Kernel{,_sf} / _Shm_Kernel
+//                         include/hgnnAgg.cuh:98-276, launched with the grid/block
+//                         geometry of HyperGAggr_device (:985-1017) -- the reference's own
+//                         balanced fused kernels recompiled for sm_100a, used as the
+//                         "reference kernel on B200" baseline row of bench.py.
+#include "hgnnAgg.cuh"
+
+#include <cstdint>
+#include <vector>
+
+namespace {
+std::vector<int> g_key, g_row, g_st, g_ed;
+}
+
+extern "C" {
+
+// Runs the reference balancer once and caches the vectors; sizes via out params.
+int ref_balance_run(int nrow, int part, const int *indptr, long long *nkey, long long *ngroup) {
+  g_key.clear(); g_row.clear(); g_st.clear(); g_ed.clear();
+  hgnn_ef_full_balance_cpu<int>(nrow, part, indptr, g_key, g_row, g_st, g_ed);
+  *nkey = (long long)g_key.size();
+  *ngroup = (long long)g_row.size();
+  return 0;
+}
+
+int ref_balance_fetch(int *key, int *row, int *st, int *ed) {
+  std::copy(g_key.begin(), g_key.end(), key);
+  std::copy(g_row.begin(), g_row.end(), row);
+  std::copy(g_st.begin(), g_st.end(), st);
+  std::copy(g_ed.begin(), g_ed.end(), ed);
+  return 0;
+}
+
+int ref_hyperaggr_host(int nrow, int feature, const int *indptr, const int *indices,
+                       const int *t_indptr, const int *t_indices, const float *in, float *out) {
+  util::hyperaggr_reference_host<int, float>(nrow, feature, indptr, indices, t_indptr, t_indices,
+                                             in, out);
+  return 0;
+}
+
+int ref_spmm_host(int nrow, int feature, int *indptr, int *indices, float *values, float *B,
+                  float *C) {
+  util::spmm_reference_host<int, float>(nrow, feature, indptr, indices, values, B, C);
+  return 0;
+}
+
+int ref_weight_grad(int nedge, int feature, const int *t_indptr, const int *t_indices,
+                    const float *grad_out, const float *feat, float *wgrad) {
+  util::hgnnbp_reference_host<int, float>(nedge, feature, t_indptr, t_indices, grad_out, feat,
+                                          wgrad);
+  return 0;
+}
+
+// Device pointers in, legacy default stream (as the reference launches).
+// variant: 0 = edge_based_full (no smem), 1 = edge_based_shm.  `out` is accumulated into
+// (the lab harness never re-zeroes it, hgnnAgg.cuh:1084-1092); the caller zero-fills.
+int ref_lab_full_gpu(int variant, int nedge, int part, int groups, int feature, int *key, int *st,
+                     int *ed, int *t_indices, float *in, float *out) {
+  const int M = 2, Nn = 32;
+  dim3 grid(CEIL(groups, M), CEIL(feature, Nn), 1);
+  if (variant == 1) {
+    dim3 block(MIN(Nn, feature), M, 1);
+    HyperGAggr_Edgefused_Balance_Shm_Kernel<int, float, M, Nn>
+        <<<grid, block, M * feature * sizeof(float)>>>(nedge, part, groups, feature, key, st, ed,
+                                                        t_indices, in, out);
+  } else if (feature >= 32) {
+    dim3 block(MIN(Nn, feature), M, 1);
+    HyperGAggr_Edgefused_Balance_Full_Kernel<int, float, M, Nn>
+        <<<grid, block>>>(nedge, groups, feature, key, st, ed, t_indices, in, out);
+  } else {
+    dim3 block(Nn, M, 1);
+    HyperGAggr_Edgefused_Balance_Full_Kernel_sf<int, float, M, Nn>
+        <<<grid, block>>>(nedge, groups, feature, key, st, ed, t_indices, in, out);
+  }
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -1,0 +1,276 @@
+"""Parity of the CUDA path (through the C-ABI) with the oracle -- runs on the B200 box.
+
+Bit-exact for integer work (balancer, CSR); <= 1e-5 relative (max-abs error over max-abs value,
+the north star's tolerance for atomic-reordered fp32 sums) against the fp64 oracle for features.
+"""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import balancer_cases, load_golden
+import hypergef_b200 as hgef
+from hypergef_b200 import HyperGraph, balance_schedule, ops, synth, _native
+from hypergef_b200.hypergraph import build_csr
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _graph(g, dev):
+    d = load_golden("graph_" + g)
+    data = SimpleNamespace(x=torch.zeros(int(d["num_nodes"]), 1), edge_index=torch.from_numpy(d["edge_index"]))
+    return d, HyperGraph(data, dev, "synthetic", ngs=int(d["ngs"]))
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+# ------------------------------------------------------------------ integer work: bit-exact
+def test_device_balancer_bit_exact(cuda_device):
+    d, names = balancer_cases()
+    for name in names:
+        bs = balance_schedule(int(d[f"{name}__ngs"]), torch.from_numpy(d[f"{name}__csrptr"]).to(cuda_device))
+        for attr, k in (("balan_key", "key"), ("balan_row", "row"), ("group_st", "st"), ("group_ed", "ed")):
+            got = getattr(bs, attr)
+            assert got.is_cuda and got.dtype == torch.int32
+            assert np.array_equal(_np(got), d[f"{name}__{k}"]), f"{name}:{k}"
+    with pytest.raises(IndexError):
+        balance_schedule(3, torch.zeros(4, dtype=torch.int32, device=cuda_device))
+
+
+def test_device_balancer_equals_host_at_scale(cuda_device):
+    rng = np.random.default_rng(2)
+    deg = rng.geometric(0.25, size=300_000)
+    deg[rng.integers(0, deg.size, 50)] = rng.integers(1000, 30000, 50)
+    deg[rng.integers(0, deg.size, 1000)] = 0
+    ptr = torch.from_numpy(np.concatenate([[0], np.cumsum(deg)]).astype(np.int32))
+    for ngs in (7, 210):
+        h, g = balance_schedule(ngs, ptr), balance_schedule(ngs, ptr.to(cuda_device))
+        for k in ("balan_key", "balan_row", "group_st", "group_ed"):
+            assert np.array_equal(getattr(h, k), _np(getattr(g, k))), (ngs, k)
+
+
+@pytest.mark.parametrize("g", ["cora", "mini", "mini_rep3"])
+def test_device_hypergraph_bit_exact(g, cuda_device):
+    d, hg = _graph(g, cuda_device)
+    for attr in ("H_csrptr", "H_colind", "H_data", "H_T_csrptr", "H_T_colind", "H_T_data",
+                 "group_key", "group_row", "group_start", "group_end"):
+        got = _np(getattr(hg, attr))
+        assert got.dtype == d[attr].dtype and np.array_equal(got, d[attr]), attr
+    assert np.array_equal(_np(hg.degE), d["degE"])                        # exact reciprocal
+    assert np.abs(_np(hg.degV) - d["degV"]).max() <= 2.5e-7 * d["degV"].max()   # torch rsqrt is not exact
+
+
+def test_device_csr_random_unsorted_duplicates(cuda_device):
+    rng = np.random.default_rng(9)
+    N, M, n = 5000, 1200, 60000
+    V, E = rng.integers(0, N, n), rng.integers(0, M, n)
+    V[:500], E[:500] = V[500:1000], E[500:1000]            # duplicates
+    E[E == 17] = 18
+    got = build_csr(torch.from_numpy(V), torch.from_numpy(E), N, M, cuda_device)
+    H, H_T = orc.scipy_incidence(V, E, N, M)
+    for a, b in zip(got, (H.indptr, H.indices, H.data, H_T.indptr, H_T.indices, H_T.data)):
+        assert np.array_equal(_np(a), b.astype(_np(a).dtype))
+    host = build_csr(torch.from_numpy(V), torch.from_numpy(E), N, M, torch.device("cpu"))
+    for a, b in zip(got, host):
+        assert torch.equal(a.cpu(), b)
+    with pytest.raises(ValueError):
+        build_csr(torch.tensor([N]), torch.tensor([0]), N, M, cuda_device)
+
+
+# ------------------------------------------------------------------ features: <= 1e-5 relative
+@pytest.mark.parametrize("g", ["mini", "mini_rep3"])
+def test_forward_matches_golden(g, cuda_device):
+    d, hg = _graph(g, cuda_device)
+    X = torch.from_numpy(d["X"]).to(cuda_device)
+    W = torch.from_numpy(d["W"]).to(cuda_device)
+    Y = hgef.HGNNAggr(hg, X, hg.degE, hg.degV, W, "sum")
+    assert orc.rel_err(_np(Y), d["Y_hgnn_f64"]) < TOL
+    Yu = hgef.UniGNNConv(hg, X)
+    assert orc.rel_err(_np(Yu), d["Y_unscaled_ref_host"]) < TOL     # the reference's own host golden
+    Yd = hgef.UniGNNConvdeg(hg, X, hg.degE, hg.degV)
+    want = orc.c_aggr_formula(d["H_T_csrptr"], d["H_T_colind"], d["X"], s1=d["degE"], a_out=d["degV"])
+    assert orc.rel_err(_np(Yd), want) < TOL
+    # the reference test's 5-argument call (test/hgnn_test.py:89)
+    assert hgef.HGNNAggr(hg, X, hg.degE, hg.degV, W).shape == Y.shape
+
+
+@pytest.mark.parametrize("F", [1, 2, 7, 12, 32, 64, 100, 128, 200, 256, 512, 516])
+def test_forward_feature_lengths(F, cuda_device):
+    """Every vector layout (lanes/row 1..32, 1/2/4 vectors per lane) and the scalar tail path."""
+    d, hg = _graph("mini", cuda_device)           # ngs=6, max hyperedge 75: light and heavy hyperedges
+    N, M = hg.num_nodes, hg.num_edges
+    X = torch.randn(N, F, generator=torch.Generator().manual_seed(F))
+    W = 0.5 + torch.rand(M, generator=torch.Generator().manual_seed(1))
+    want = orc.c_aggr_formula(d["H_T_csrptr"], d["H_T_colind"], X, s1=d["degE"], s2=W, a_out=d["degV"])
+    Y = ops.hgnnaggr(hg.group_key, hg.group_row, hg.group_start, hg.group_end, hg.H_T_csrptr, hg.H_T_colind,
+                     X.to(cuda_device), hg.degE, hg.degV, W.to(cuda_device))
+    assert Y.shape == (N, F) and orc.rel_err(_np(Y), want) < TOL
+
+
+def test_plan_sees_heavy_hyperedges_and_schedules_agree(cuda_device):
+    d, hg = _graph("mini_rep3", cuda_device)
+    plan = ops.get_plan(hg.group_key, hg.group_row, hg.group_start, hg.group_end, hg.H_T_colind,
+                        hg.num_nodes, hg.num_edges)
+    assert plan.canonical and plan.nseg == d["group_key"].size - 1
+    w = np.ceil(np.diff(d["H_T_csrptr"]) / int(d["ngs"])).astype(int)
+    assert plan.nheavy_edges == int((w > 1).sum()) and plan.nheavy_segs == int(w[w > 1].sum())
+    X = torch.from_numpy(d["X"]).to(cuda_device)
+    Y1 = ops.aggregate(plan, X, s1=hg.degE, a_out=hg.degV)
+    # the literal reference schedule (one work unit per balancer group) through the C-ABI
+    Y2 = torch.empty_like(Y1)
+    _native.call("hg_aggr_groups", hg.num_nodes, hg.group_row.numel(), hg.group_key.data_ptr(),
+                 hg.group_row.data_ptr(), hg.group_start.data_ptr(), hg.group_end.data_ptr(),
+                 hg.H_T_colind.data_ptr(), X.data_ptr(), hg.degE.data_ptr(), None, hg.degV.data_ptr(), None,
+                 Y2.data_ptr(), X.shape[1], 0, 0, torch.cuda.current_stream().cuda_stream)
+    want = orc.c_aggr_groups(d["group_key"], d["group_row"], d["group_start"], d["group_end"], d["H_T_colind"],
+                             d["X"], s1=d["degE"], a_out=d["degV"])
+    assert orc.rel_err(_np(Y1), want) < TOL and orc.rel_err(_np(Y2), want) < TOL
+    for flag in (_native.HG_FORCE_SCALAR,):
+        Y3 = ops.aggregate(plan, X, s1=hg.degE, a_out=hg.degV, flags=flag)
+        assert orc.rel_err(_np(Y3), want) < TOL
+    # accumulate flag: Y += op(X)
+    Y4 = ops.aggregate(plan, X, s1=hg.degE, a_out=hg.degV, out=Y1.clone(), flags=_native.HG_ACCUMULATE)
+    assert orc.rel_err(_np(Y4), 2 * want) < TOL
+
+
+def test_non_canonical_groups_keep_reference_meaning(cuda_device):
+    """User-built group arrays that are not the balancer's full cross product run with the
+    literal semantics of hgnnaggr_cuda.cu:14-47 (gather seg st[g], scatter seg ed[g])."""
+    d, hg = _graph("mini", cuda_device)
+    rng = np.random.default_rng(0)
+    keep = np.sort(rng.choice(d["group_row"].size, size=d["group_row"].size // 2, replace=False))
+    row, st, ed = (torch.from_numpy(d[k][keep]).to(cuda_device) for k in ("group_row", "group_start", "group_end"))
+    plan = ops.get_plan(hg.group_key, row, st, ed, hg.H_T_colind, hg.num_nodes, hg.num_edges)
+    assert not plan.canonical
+    X = torch.from_numpy(d["X"]).to(cuda_device)
+    Y = ops.aggregate(plan, X, s1=hg.degE, a_out=hg.degV)
+    want = orc.c_aggr_groups(d["group_key"], d["group_row"][keep], d["group_start"][keep], d["group_end"][keep],
+                             d["H_T_colind"], d["X"], s1=d["degE"], a_out=d["degV"])
+    assert orc.rel_err(_np(Y), want) < TOL
+
+
+def test_backward_transpose_and_reference_modes(cuda_device):
+    d, hg = _graph("mini", cuda_device)
+    N, M = hg.num_nodes, hg.num_edges
+    F = 16
+    gen = torch.Generator().manual_seed(5)
+    X0, G0 = torch.randn(N, F, generator=gen), torch.randn(N, F, generator=gen)
+    W0 = 0.5 + torch.rand(M, generator=gen)
+    # fp64 autograd through the PyG-equivalent conv (model/pygnn/hgnn.py:30-37)
+    E = torch.from_numpy(np.repeat(np.arange(M), np.diff(d["H_T_csrptr"]))).long()
+    V = torch.from_numpy(d["H_T_colind"].astype(np.int64))
+    Xd, Wd = X0.double().requires_grad_(True), W0.double().requires_grad_(True)
+    Yd = orc.torch_hgnn_conv(Xd, V, E, torch.from_numpy(d["degE"]).double(), torch.from_numpy(d["degV"]).double(),
+                             Wd, N, M)
+    Yd.backward(G0.double())
+    X = X0.to(cuda_device).requires_grad_(True)
+    W = W0.to(cuda_device).requires_grad_(True)
+    assert hgef.get_backward_mode() == "transpose"
+    Y = hgef.HGNNAggr(hg, X, hg.degE, hg.degV, W, "sum")
+    Y.backward(G0.to(cuda_device))
+    assert orc.rel_err(_np(Y), Yd.detach().numpy()) < TOL
+    assert orc.rel_err(_np(X.grad), Xd.grad.numpy()) < TOL
+    assert orc.rel_err(_np(W.grad), Wd.grad.numpy()) < TOL           # the reference returns no W grad
+    # reference mode: backward == forward applied to grad_out (hgnnaggr.cc:58-60)
+    hgef.set_backward_mode("reference")
+    try:
+        X2 = X0.to(cuda_device).requires_grad_(True)
+        hgef.HGNNAggr(hg, X2, hg.degE, hg.degV, W.detach(), "sum").backward(G0.to(cuda_device))
+        want = orc.c_aggr_formula(d["H_T_csrptr"], d["H_T_colind"], G0, s1=d["degE"], s2=W0, a_out=d["degV"])
+        assert orc.rel_err(_np(X2.grad), want) < TOL
+    finally:
+        hgef.set_backward_mode("transpose")
+    # un-scaled operator is symmetric: both modes coincide (unignnaggr.cc:72-74)
+    X3 = X0.to(cuda_device).requires_grad_(True)
+    hgef.UniGNNConv(hg, X3).backward(G0.to(cuda_device))
+    assert orc.rel_err(_np(X3.grad), orc.c_aggr_formula(d["H_T_csrptr"], d["H_T_colind"], G0)) < TOL
+
+
+def test_mean_and_max_variants(cuda_device):
+    d, hg = _graph("mini", cuda_device)
+    N, M, F = hg.num_nodes, hg.num_edges, 40
+    gen = torch.Generator().manual_seed(8)
+    X0, G0 = torch.randn(N, F, generator=gen), torch.randn(N, F, generator=gen)
+    W0 = 0.5 + torch.rand(M, generator=gen)
+    X, W = X0.to(cuda_device).requires_grad_(True), W0.to(cuda_device)
+    Ym = hgef.HGNNAggr(hg, X, hg.degE, hg.degV, W, "mean")
+    want = orc.c_aggr_formula(d["H_T_csrptr"], d["H_T_colind"], X0, s1=d["degE"], s2=W0, a_out=d["degV"], reduce="mean")
+    assert orc.rel_err(_np(Ym), want) < TOL
+    Ym.backward(G0.to(cuda_device))
+    wantg = orc.c_aggr_formula(d["H_T_csrptr"], d["H_T_colind"], G0, s1=d["degE"], s2=W0, a_out=d["degV"], reduce="mean")
+    assert orc.rel_err(_np(X.grad), wantg) < TOL
+    X.grad = None
+    out, rec = hgef.hgnnaggr.hgnnaggr_max(hg.H_T_csrptr, hg.H_T_colind, X, hg.degE, hg.degV, W)
+    wy, wrec = orc.c_aggr_max(d["H_T_csrptr"], d["H_T_colind"], X0, s1=d["degE"], s2=W0, a_out=d["degV"])
+    assert orc.rel_err(_np(out), wy) < TOL and np.array_equal(_np(rec), wrec)
+    out.backward(G0.to(cuda_device))
+    wdx = orc.c_aggr_max_bwd(d["H_T_csrptr"], d["H_T_colind"], G0, wrec, s1=d["degE"], s2=W0, a_out=d["degV"])
+    assert orc.rel_err(_np(X.grad), wdx) < TOL
+
+
+@pytest.mark.parametrize("shape,F", [("cora", 32), ("pubmed", 64), ("dblp", 128), ("walmart", 32)])
+def test_baseline_shapes_against_oracle(shape, F, cuda_device):
+    """BASELINE.json configs at their literal sizes (C1-C4); walmart plants a 12345-member hyperedge."""
+    data = synth.make_shape(shape, seed=0)
+    hg = HyperGraph(data, cuda_device, data.dataset)
+    if shape == "walmart":
+        assert int((hg.H_T_csrptr[1:] - hg.H_T_csrptr[:-1]).max()) > 10_000
+    X = torch.randn(hg.num_nodes, F, generator=torch.Generator().manual_seed(1))
+    Y = hgef.HGNNAggr(hg, X.to(cuda_device), hg.degE, hg.degV, torch.ones(hg.num_edges, device=cuda_device))
+    want = orc.c_aggr_formula(_np(hg.H_T_csrptr), _np(hg.H_T_colind), X, s1=_np(hg.degE), a_out=_np(hg.degV))
+    assert orc.rel_err(_np(Y), want) < TOL
+    # balancer at the literal size is bit-exact with the C oracle
+    b = orc.c_balancer(hg.ngs, _np(hg.H_T_csrptr))
+    assert np.array_equal(_np(hg.group_key), b.balan_key) and np.array_equal(_np(hg.group_end), b.group_ed)
+
+
+def test_full_size_properties(cuda_device):
+    """Pubmed-shaped x64 (the bench workload) at F=128: properties that need no CPU oracle --
+    linearity, the adjoint identity <A x, z> = <x, A^T z>, and the column checksum
+    1^T (H H^T X) = sum_e |e| (H^T X)_e."""
+    data = synth.make_shape("pubmed", replicas=64, seed=0, device=cuda_device)
+    hg = HyperGraph(data, cuda_device, "pubmed")
+    N, F = hg.num_nodes, 128
+    gen = torch.Generator(device=cuda_device).manual_seed(0)
+    X, Z = (torch.randn(N, F, device=cuda_device, generator=gen) for _ in range(2))
+    plan = ops.get_plan(hg.group_key, hg.group_row, hg.group_start, hg.group_end, hg.H_T_colind, N, hg.num_edges)
+    A = lambda x, **kw: ops.aggregate(plan, x, s1=hg.degE, **kw)
+    y1, y2 = A(X, a_out=hg.degV), A(Z, a_out=hg.degV)
+    y3 = A(2.0 * X - 3.0 * Z, a_out=hg.degV)
+    assert ((y3 - (2.0 * y1 - 3.0 * y2)).abs().max() / y3.abs().max()).item() < TOL
+    lhs = (y1.double() * Z.double()).sum()
+    rhs = (X.double() * A(Z, a_in=hg.degV).double()).sum()
+    assert abs((lhs - rhs) / lhs).item() < 1e-6
+    yu = ops.aggregate(plan, X)
+    deg = (hg.H_T_csrptr[1:] - hg.H_T_csrptr[:-1]).double()
+    rows = torch.repeat_interleave(torch.arange(hg.num_edges, device=cuda_device), deg.long())
+    xe = torch.zeros(hg.num_edges, F, dtype=torch.float64, device=cuda_device).index_add_(
+        0, rows, X.double()[hg.H_T_colind.long()])
+    want = (xe * deg[:, None]).sum(0)
+    assert ((yu.double().sum(0) - want).abs().max() / want.abs().max()).item() < 1e-6
+
+
+# ------------------------------------------------------------------ error behaviour
+def test_errors_raise_instead_of_aborting(cuda_device):
+    d, hg = _graph("mini", cuda_device)
+    X = torch.from_numpy(d["X"]).to(cuda_device)
+    with pytest.raises(TypeError):
+        hgef.UniGNNConv(hg, X.double())
+    with pytest.raises(ValueError):
+        hgef.UniGNNConv(hg, X[:-1])
+    with pytest.raises(ValueError):
+        hgef.UniGNNConvdeg(hg, X, hg.degE[:-1], hg.degV)
+    bad = hg.H_T_colind.clone()
+    bad[3] = hg.num_nodes                                   # out-of-range vertex id
+    with pytest.raises(_native.HgefGraphError):
+        ops.get_plan(hg.group_key, hg.group_row, hg.group_start, hg.group_end, bad, hg.num_nodes, hg.num_edges)
+    badk = hg.group_key.clone()
+    badk[2] = badk[1] - 1                                   # key not monotone
+    with pytest.raises(_native.HgefGraphError):
+        ops.get_plan(badk, hg.group_row, hg.group_start, hg.group_end, hg.H_T_colind, hg.num_nodes, hg.num_edges)
+    assert _native.lib().hg_device_cc(0) == 100             # B200 = sm_100

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhgef_b200.so")
 
 HG_OK, HG_EINVAL, HG_ECUDA, HG_ENOMEM, HG_EEMPTY, HG_EGRAPH = range(6)
-HG_ACCUMULATE, HG_FORCE_SCALAR = 1, 4
+HG_ACCUMULATE, HG_FORCE_SCALAR, HG_TWO_PASS = 1, 4, 8
 
 
 class HgefBuildError(ImportError):
@@ -43,6 +43,7 @@ SIGNATURES = {
     "hg_plan_create": [C.POINTER(_vp), _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _int, _vp],
     "hg_plan_destroy": [_vp],
     "hg_plan_info": [_vp, _pi64, _pi64, _pi64, _pi32],
+    "hg_plan_check": [_vp, _vp],
     "hg_aggr_forward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp],
     "hg_aggr_groups": [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32,
                        _int, _vp],

@@ -120,6 +120,42 @@ __global__ void heavy_list_kernel(int64_t nseg, const int32_t *__restrict__ heav
   if (s < nseg && heavy_flag[s]) heavy_segs[heavy_pos[s] - 1] = (int32_t)s;
 }
 
+// occurrence count and first position (in H_T_colind order) of every vertex
+__global__ void vertex_touch_kernel(int64_t nnz, const int32_t *__restrict__ colind,
+                                    int32_t *__restrict__ cnt, int32_t *__restrict__ minpos) {
+  int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (p >= nnz) return;
+  int32_t v = colind[p];
+  atomicAdd(cnt + v, 1);
+  atomicMin(minpos + v, (int32_t)p);
+}
+
+__global__ void cflag_kernel(int64_t nnz, const int32_t *__restrict__ colind,
+                             const int32_t *__restrict__ cnt, const int32_t *__restrict__ minpos,
+                             int32_t *__restrict__ cflag) {
+  int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (p >= nnz) return;
+  int32_t v = colind[p];
+  uint32_t c = (uint32_t)v;
+  if (minpos[v] == (int32_t)p) c |= 0x80000000u;
+  if (cnt[v] == 1) c |= 0x40000000u;
+  cflag[p] = (int32_t)c;
+}
+
+__global__ void iso_flag_kernel(int64_t n, const int32_t *__restrict__ cnt, int32_t *__restrict__ iso,
+                                int32_t *__restrict__ excl) {
+  int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  iso[v] = cnt[v] == 0 ? 1 : 0;
+  excl[v] = cnt[v] == 1 ? 1 : 0;
+}
+
+__global__ void iso_list_kernel(int64_t n, const int32_t *__restrict__ iso,
+                                const int32_t *__restrict__ pos, int32_t *__restrict__ list) {
+  int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (v < n && iso[v]) list[pos[v] - 1] = (int32_t)v;
+}
+
 #define GRID(n) (unsigned)ceil_div<int64_t>((n), 256), 256
 
 template <typename In, typename Out, typename Op, typename T>
@@ -140,6 +176,39 @@ int inclusive_sum(In in, Out out, int64_t n, cudaStream_t s) {
   DevBuf<char> ws;
   HG_CUDA_TRY(ws.alloc(bytes));
   HG_CUDA_TRY(cub::DeviceScan::InclusiveSum(ws.p, bytes, in, out, n, s));
+  HG_CUDA_TRY(cudaStreamSynchronize(s));
+  return HG_OK;
+}
+
+int inclusive_sum_i32(const int32_t *in, int32_t *out, int64_t n, cudaStream_t s);
+
+// first-touch / single-writer flags for the fused kernel (vertex ids must fit 30 bits)
+int build_fused(hgPlan *p, cudaStream_t s) {
+  const int64_t N = p->num_nodes, Z = p->nnz;
+  if (N >= (int64_t(1) << 30) || Z == 0 || N == 0) return HG_OK;  // cflag stays NULL: two-pass path
+  DevBuf<int32_t> cnt, minpos, iso, excl, pos;
+  HG_CUDA_TRY(cnt.alloc(N)); HG_CUDA_TRY(minpos.alloc(N)); HG_CUDA_TRY(iso.alloc(N));
+  HG_CUDA_TRY(excl.alloc(N)); HG_CUDA_TRY(pos.alloc(N));
+  HG_CUDA_TRY(cudaMemsetAsync(cnt.p, 0, (size_t)N * sizeof(int32_t), s));
+  HG_CUDA_TRY(cudaMemsetAsync(minpos.p, 0x7f, (size_t)N * sizeof(int32_t), s));
+  HG_CUDA_TRY(cudaMalloc((void **)&p->cflag, (size_t)Z * sizeof(int32_t)));
+  HG_CUDA_TRY(cudaMalloc((void **)&p->ctrl, (size_t)(p->nseg + 64) * sizeof(int32_t)));
+  HG_CUDA_TRY(cudaMemsetAsync(p->ctrl, 0, (size_t)(p->nseg + 64) * sizeof(int32_t), s));
+  vertex_touch_kernel<<<GRID(Z), 0, s>>>(Z, p->colind, cnt.p, minpos.p);
+  cflag_kernel<<<GRID(Z), 0, s>>>(Z, p->colind, cnt.p, minpos.p, p->cflag);
+  iso_flag_kernel<<<GRID(N), 0, s>>>(N, cnt.p, iso.p, excl.p);
+  HG_CUDA_TRY(cudaGetLastError());
+  int32_t niso = 0, nexcl = 0;
+  if (int rc = inclusive_sum_i32(excl.p, pos.p, N, s)) return rc;
+  HG_CUDA_TRY(cudaMemcpy(&nexcl, pos.p + (N - 1), sizeof(int32_t), cudaMemcpyDeviceToHost));
+  if (int rc = inclusive_sum_i32(iso.p, pos.p, N, s)) return rc;
+  HG_CUDA_TRY(cudaMemcpy(&niso, pos.p + (N - 1), sizeof(int32_t), cudaMemcpyDeviceToHost));
+  p->niso = niso; p->nexcl = nexcl;
+  if (niso) {
+    HG_CUDA_TRY(cudaMalloc((void **)&p->iso_list, (size_t)niso * sizeof(int32_t)));
+    iso_list_kernel<<<GRID(N), 0, s>>>(N, iso.p, pos.p, p->iso_list);
+    HG_CUDA_TRY(cudaGetLastError());
+  }
   HG_CUDA_TRY(cudaStreamSynchronize(s));
   return HG_OK;
 }
@@ -225,7 +294,11 @@ int build(hgPlan *p, cudaStream_t s) {
     HG_CUDA_TRY(cudaGetLastError());
     HG_CUDA_TRY(cudaStreamSynchronize(s));
   }
-  return HG_OK;
+  return build_fused(p, s);
+}
+
+int inclusive_sum_i32(const int32_t *in, int32_t *out, int64_t n, cudaStream_t s) {
+  return inclusive_sum(in, out, n, s);
 }
 
 }  // namespace
@@ -269,6 +342,9 @@ int hg_plan_destroy(hgPlan *p) {
   cudaFree(p->seg_edge);
   cudaFree(p->seg_slot);
   cudaFree(p->heavy_segs);
+  cudaFree(p->cflag);
+  cudaFree(p->iso_list);
+  cudaFree(p->ctrl);
   cudaFree(p->scratch);
   delete p;
   return HG_OK;

@@ -16,6 +16,13 @@ struct hgPlan {
   int64_t nheavy_edges = 0, nheavy_segs = 0;
   int32_t canonical = 0;          // groups == full cross product in balancer order
   int32_t max_seg_len = 0;
+  // fused persistent kernel (hgef_fused.cu)
+  int32_t *cflag = nullptr;       // [nnz] colind with bit31 = first occurrence of the vertex in
+                                  //       H_T_colind order, bit30 = the vertex has exactly one
+                                  //       occurrence (its Y row has a single writer)
+  int32_t *iso_list = nullptr;    // [niso] vertices in no hyperedge (their Y row is just zero)
+  int64_t niso = 0, nexcl = 0;
+  int32_t *ctrl = nullptr;        // [nseg + 64] per-call tile counter, give-up flag, block counts, tile flags
   // scratch: partial hyperedge features of heavy hyperedges, [nheavy_edges, F]; L2-resident
   float *scratch = nullptr;
   size_t scratch_floats = 0;

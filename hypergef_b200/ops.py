@@ -124,6 +124,10 @@ class Plan:
         self.nseg, self.nheavy_edges, self.nheavy_segs = nseg.value, he.value, hs.value
         self.canonical = bool(canon.value)
 
+    def check(self) -> None:
+        """Synchronise and raise if any launch issued with this plan faulted (hg_plan_check)."""
+        _native.call("hg_plan_check", self.handle, torch.cuda.current_stream(self.device_index).cuda_stream)
+
     def __del__(self):
         h, self.handle = getattr(self, "handle", None), None
         if h:

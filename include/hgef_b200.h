@@ -107,10 +107,16 @@ HG_API int hg_plan_destroy(hgPlan *plan);
 HG_API int hg_plan_info(const hgPlan *plan, int64_t *nseg, int64_t *nheavy_edges,
                         int64_t *nheavy_segs, int32_t *canonical);
 
+/* Synchronises `stream` and reports (HG_ECUDA) any fault of the launches issued with this plan,
+ * including the fused kernel's bounded-wait give-up.  The reference has no equivalent: it never
+ * checks a launch (hgnnaggr_cuda.cu:383-404). */
+HG_API int hg_plan_check(hgPlan *plan, void *stream);
+
 /* flags for hg_aggr_* */
 enum {
   HG_ACCUMULATE = 1,     /* do not zero-fill Y first (reference: torch::zeros, hgnnaggr_cuda.cu:374) */
-  HG_FORCE_SCALAR = 4    /* disable the 128-bit path (testing) */
+  HG_FORCE_SCALAR = 4,   /* disable the 128-bit path (testing) */
+  HG_TWO_PASS = 8        /* memset + segment kernel instead of the single persistent launch (ablation) */
 };
 
 /* ------------------------------------------------------------------------- *

@@ -110,6 +110,12 @@ def test_forward_feature_lengths(F, cuda_device):
     Y = ops.hgnnaggr(hg.group_key, hg.group_row, hg.group_start, hg.group_end, hg.H_T_csrptr, hg.H_T_colind,
                      X.to(cuda_device), hg.degE, hg.degV, W.to(cuda_device))
     assert Y.shape == (N, F) and orc.rel_err(_np(Y), want) < TOL
+    # the output buffer is NOT pre-zeroed by the caller: garbage in it must not leak through
+    plan = ops.get_plan(hg.group_key, hg.group_row, hg.group_start, hg.group_end, hg.H_T_colind, N, M)
+    out = torch.full((N, F), float("nan"), device=cuda_device)
+    ops.aggregate(plan, X.to(cuda_device), s1=hg.degE, s2=W.to(cuda_device), a_out=hg.degV, out=out)
+    plan.check()
+    assert orc.rel_err(_np(out), want) < TOL
 
 
 def test_plan_sees_heavy_hyperedges_and_schedules_agree(cuda_device):
@@ -130,9 +136,10 @@ def test_plan_sees_heavy_hyperedges_and_schedules_agree(cuda_device):
     want = orc.c_aggr_groups(d["group_key"], d["group_row"], d["group_start"], d["group_end"], d["H_T_colind"],
                              d["X"], s1=d["degE"], a_out=d["degV"])
     assert orc.rel_err(_np(Y1), want) < TOL and orc.rel_err(_np(Y2), want) < TOL
-    for flag in (_native.HG_FORCE_SCALAR,):
+    for flag in (_native.HG_FORCE_SCALAR, _native.HG_TWO_PASS):     # scalar tail path; memset + 2-pass form
         Y3 = ops.aggregate(plan, X, s1=hg.degE, a_out=hg.degV, flags=flag)
         assert orc.rel_err(_np(Y3), want) < TOL
+    plan.check()
     # accumulate flag: Y += op(X)
     Y4 = ops.aggregate(plan, X, s1=hg.degE, a_out=hg.degV, out=Y1.clone(), flags=_native.HG_ACCUMULATE)
     assert orc.rel_err(_np(Y4), 2 * want) < TOL
@@ -246,6 +253,7 @@ def test_full_size_properties(cuda_device):
     lhs = (y1.double() * Z.double()).sum()
     rhs = (X.double() * A(Z, a_in=hg.degV).double()).sum()
     assert abs((lhs - rhs) / lhs).item() < 1e-6
+    plan.check()
     yu = ops.aggregate(plan, X)
     deg = (hg.H_T_csrptr[1:] - hg.H_T_csrptr[:-1]).double()
     rows = torch.repeat_interleave(torch.arange(hg.num_edges, device=cuda_device), deg.long())

@@ -1,0 +1,38 @@
+#!/usr/bin/env python
+"""Quick kernel timing for tuning: python tools/tune.py --features 32,128,512 --replicas 64 [--two-pass]"""
+import argparse, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import hypergef_b200 as hgef
+from hypergef_b200 import ops, synth, _native
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--features", default="32,64,128,256,512")
+ap.add_argument("--shape", default="pubmed")
+ap.add_argument("--replicas", type=int, default=64)
+ap.add_argument("--iters", type=int, default=20)
+ap.add_argument("--two-pass", action="store_true")
+ap.add_argument("--tag", default="")
+args = ap.parse_args()
+dev = torch.device("cuda:0")
+data = synth.make_shape(args.shape, replicas=args.replicas, seed=0, device=dev)
+hg = hgef.HyperGraph(data, dev, data.dataset)
+N, M, Z = hg.num_nodes, hg.num_edges, hg.H_T_colind.numel()
+plan = ops.get_plan(hg.group_key, hg.group_row, hg.group_start, hg.group_end, hg.H_T_colind, N, M)
+W = torch.ones(M, device=dev)
+flags = _native.HG_TWO_PASS if args.two_pass else 0
+out = []
+for F in [int(f) for f in args.features.split(",")]:
+    X = torch.randn(N, F, device=dev); Y = torch.empty(N, F, device=dev)
+    for _ in range(3):
+        ops.aggregate(plan, X, s1=hg.degE, s2=W, a_out=hg.degV, out=Y, flags=flags)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.iters):
+        ops.aggregate(plan, X, s1=hg.degE, s2=W, a_out=hg.degV, out=Y, flags=flags)
+    b.record(); torch.cuda.synchronize(); plan.check()
+    us = a.elapsed_time(b) / args.iters * 1e3
+    balg = 8 * F * N + 4 * Z + 12 * M + 4 * N + 4
+    out.append(f"F={F}: {us:8.1f} us {balg / us / 1e3:7.1f} GB/s ({balg / us / 1e3 / 6536 * 100:4.1f}%)")
+    del X, Y
+print(f"[{args.tag} {args.shape}x{args.replicas} N={N} Z={Z} heavy={plan.nheavy_edges}] " + " | ".join(out), flush=True)

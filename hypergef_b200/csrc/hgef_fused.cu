@@ -26,6 +26,7 @@
 // Heavy hyperedges (w > 1 segments) publish partial sums to scratch here; the second,
 // small launch (seg_pass2 with the same flags) scatters them.
 #include <cstdlib>
+#include <type_traits>
 
 #include "hgef_aggr.cuh"
 
@@ -34,7 +35,7 @@ namespace {
 using namespace dev;
 
 constexpr uint32_t kFirst = 0x80000000u, kExcl = 0x40000000u, kIdMask = 0x3fffffffu;
-constexpr int kIdxCap = 3072;  // staged column indices per tile (ints); beyond that: global reads
+constexpr int kIdxCap = 96;  // staged rows per warp tile (index, a_out, a_in); beyond that: global reads
 
 struct FusedArgs {
   Args a;
@@ -43,6 +44,7 @@ struct FusedArgs {
                         // (32 tiles per block), [8 + nblk + t] done flag of tile t
   int64_t niso;
   int32_t ntiles, tile_segs, nblk;
+  // TIMING EXPERIMENT ONLY (HGEF_UNSAFE_NOSYNC=1): skip publish / wait
 };
 
 __device__ __forceinline__ int ld_acquire(const int *p) {
@@ -58,8 +60,11 @@ __device__ __forceinline__ int ld_relaxed(const int *p) {
 __device__ __forceinline__ void st_release(int *p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ void red_release_inc(int *p) {
-  asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p) : "memory");
+__device__ __forceinline__ void st_relaxed(int *p, int v) {
+  asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_relaxed_inc(int *p) {
+  asm volatile("red.relaxed.gpu.global.add.s32 [%0], 1;" ::"l"(p) : "memory");
 }
 
 // Wait (whole warp) until the zero-fill of every tile <= t is complete.  Progress is tracked in
@@ -94,6 +99,10 @@ __device__ __forceinline__ void wait_zero_fill(int32_t *ctrl, int nblk, int t, i
   asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 
+__device__ __forceinline__ void cp_async16(float *smem_dst, const float *gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void st_zero_v4(float *p) {
   asm volatile("st.global.v4.f32 [%0], {%1, %1, %1, %1};" ::"l"(p), "f"(0.0f) : "memory");
 }
@@ -103,183 +112,234 @@ __device__ __forceinline__ void st_v4(float *p, float4 v) {
                : "memory");
 }
 
-template <int VPL>
-__global__ void __launch_bounds__(kThreads) fused_kernel(const FusedArgs fa) {
-  extern __shared__ int32_t smem[];
-  const Args &a = fa.a;
-  const int T = fa.tile_segs;
-  const int buf_ints = 3 * T + 1 + kIdxCap;  // per tile buffer: key[T+1] slot[T] scale[T] idx[kIdxCap]
-  __shared__ int s_tile[2], s_cursor;
+// One SUB-WARP of SW lanes walks the rows of its run of segments; lane l of the sub-warp holds
+// columns l*4 + j*SW*4 .. +3, j < VPL.  SW = 32 (whole warp per row, no divergence) for F >= 128.
+template <int SW, int VPL>
+struct Geo {
+  static constexpr int kSub = 32 / SW;        // row streams per warp
+  static constexpr int kColStride = SW * 4;   // floats between a lane's vectors
+  static constexpr int kUnroll = (SW * VPL >= 32 ? 8 : 4) / VPL;  // rows per pipeline step: 8 (rows >= 512 B)
+                                                               // or 4 x 16 B per lane in flight
+};
 
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int lpr = a.lpr, groups = 32 / lpr, grp = lane / lpr;
-  const int col = (lane & (lpr - 1)) * 4;
+constexpr int kTileMax = 32;   // segments per warp tile (one staging lane per segment)
+constexpr int kHdrInts = 100;  // key[33] slot[32] scale[32], padded to 16 B
+constexpr int kBufInts = kHdrInts + 3 * kIdxCap;  // + idx[] wout[] win[]
+
+template <int SW, int VPL, bool EXACT>
+__device__ __forceinline__ bool col_ok(int col, int j, int F) {
+  return EXACT || col + j * Geo<SW, VPL>::kColStride < F;
+}
+
+// Persistent kernel, every WARP autonomous (no CTA-wide barrier anywhere).  A warp claims small
+// tiles of consecutive segments from the global counter and runs a two-deep software pipeline:
+//     claim t'  ->  stage t' (segment bounds, flagged column indices, per-row scales) in its
+//     private shared-memory buffer  ->  zero-fill the rows t' touches first  ->  publish (one
+//     release fence)  ->  wait until every tile <= t is published  ->  stream tile t (claimed
+//     one iteration earlier): gather / reduce / scatter  ->  t = t'
+// so the wait is normally already satisfied.  Inside a tile the X rows stream through a private
+// shared-memory ring with cp.async, the loads of step k+1 issued before step k is consumed, and
+// every per-row quantity the hot loops need (index, flags, a_in, a_out) comes from shared
+// memory, so the only long-latency operations in flight are the feature rows themselves.
+template <int SW, int VPL, bool EXACT>
+__global__ void __launch_bounds__(kThreads) fused_kernel(const FusedArgs fa) {
+  using G = Geo<SW, VPL>;
+  extern __shared__ __align__(16) int32_t smem[];
+  const Args &a = fa.a;
+  const int T = fa.tile_segs;                      // <= 31
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int32_t *wbuf = smem + warp * 2 * kBufInts;      // this warp's two tile buffers
+  float *ring = reinterpret_cast<float *>(smem + kWarpsPerBlock * 2 * kBufInts) +
+                warp * (2 * G::kUnroll * VPL * 32 * 4);  // this warp's cp.async landing ring
+  const int sub = lane / SW;
+  const int col = (lane % SW) * 4;
   const int F = a.F;
   const int64_t S = a.nwork;
   int *counter = fa.ctrl, *blk_cnt = fa.ctrl + 8, *done = fa.ctrl + 8 + fa.nblk;
-  int blk_wm = 0;  // per warp: blocks [0, blk_wm) are known to be completely zero-filled
+  int blk_wm = 0;  // blocks [0, blk_wm) are known to be completely zero-filled
 
-  // phase 0 of tile `t` into buffer `b`: stage, zero-fill first-touched rows, publish.
-  auto phase0 = [&](int t, int b) {
-    int32_t *s_key = smem + b * buf_ints, *s_slot = s_key + T + 1;
-    float *s_scale = reinterpret_cast<float *>(s_slot + T);
-    int32_t *s_idx = reinterpret_cast<int32_t *>(s_scale + T);
+  auto claim = [&]() {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(counter, 1);
+    return __shfl_sync(kFull, t, 0);
+  };
+  // stage tile t into buffer b, zero-fill its first-touched rows, publish
+  auto produce = [&](int t, int b) {
+    int32_t *s_key = wbuf + b * kBufInts, *s_slot = s_key + 33;
+    float *s_scale = reinterpret_cast<float *>(s_slot + 32);
+    int32_t *s_idx = s_key + kHdrInts;
+    float *s_wout = reinterpret_cast<float *>(s_idx + kIdxCap), *s_win = s_wout + kIdxCap;
     const int64_t s0 = (int64_t)t * T;
     const int nseg = (int)min((int64_t)T, S - s0);
-    const int32_t p0 = __ldg(a.key + s0), p1 = __ldg(a.key + s0 + nseg);
-    for (int i = tid; i <= nseg; i += kThreads) s_key[i] = __ldg(a.key + s0 + i);
-    for (int i = tid; i < nseg; i += kThreads) {
-      s_slot[i] = __ldg(a.seg_slot + s0 + i);
-      s_scale[i] = edge_scale(a, __ldg(a.seg_edge + s0 + i));
+    int32_t k = 0;
+    if (lane <= nseg) k = __ldg(a.key + s0 + lane);
+    if (lane < nseg) {
+      s_slot[lane] = __ldg(a.seg_slot + s0 + lane);
+      s_scale[lane] = edge_scale(a, __ldg(a.seg_edge + s0 + lane));
     }
+    if (lane <= nseg) s_key[lane] = k;
+    const int32_t p0 = __shfl_sync(kFull, k, 0), p1 = __shfl_sync(kFull, k, nseg);
     const int nidx = min(p1 - p0, kIdxCap);
-    for (int i = tid; i < nidx; i += kThreads) s_idx[i] = __ldg(fa.cflag + p0 + i);
-    __syncthreads();
-    const int rows_per_pass = kThreads / lpr;
-    const int rgrp = tid / lpr;
-    for (int32_t pb = p0; pb < p1; pb += rows_per_pass) {
-      const int32_t p = pb + rgrp;
+    for (int i = lane; i < nidx; i += 32) {
+      const uint32_t c = (uint32_t)__ldg(fa.cflag + p0 + i);
+      s_idx[i] = (int32_t)c;
+      s_wout[i] = a.a_out ? __ldg(a.a_out + (c & kIdMask)) : 1.0f;
+      s_win[i] = a.a_in ? __ldg(a.a_in + (c & kIdMask)) : 1.0f;
+    }
+    __syncwarp();
+    for (int32_t pb = p0; pb < p1; pb += G::kSub) {
+      const int32_t p = pb + sub;
       if (p < p1) {
         const uint32_t c = (uint32_t)(p - p0 < kIdxCap ? s_idx[p - p0] : __ldg(fa.cflag + p));
         if ((c & kFirst) && !(c & kExcl)) {
           float *yp = a.Y + (int64_t)(c & kIdMask) * F + col;
 #pragma unroll
           for (int j = 0; j < VPL; ++j)
-            if (col + j * 128 < F) st_zero_v4(yp + j * 128);
+            if (col_ok<SW, VPL, EXACT>(col, j, F)) st_zero_v4(yp + j * G::kColStride);
         }
       }
     }
-    // this tile's share of the vertices that no hyperedge touches
+    // ... and this tile's share of the vertices that no hyperedge touches
     const int64_t i0 = fa.niso * t / fa.ntiles, i1 = fa.niso * (t + 1) / fa.ntiles;
-    for (int64_t i = i0 + rgrp; i < i1; i += rows_per_pass) {
+    for (int64_t i = i0 + sub; i < i1; i += G::kSub) {
       float *yp = a.Y + (int64_t)__ldg(fa.iso + i) * F + col;
 #pragma unroll
       for (int j = 0; j < VPL; ++j)
-        if (col + j * 128 < F) st_zero_v4(yp + j * 128);
+        if (col_ok<SW, VPL, EXACT>(col, j, F)) st_zero_v4(yp + j * G::kColStride);
     }
-    __syncthreads();  // all zero stores of the CTA are ordered before the release below
-    if (tid == 0) {
-      st_release(done + t, 1);
-      red_release_inc(blk_cnt + (t >> 5));
+    __syncwarp();  // the lanes' zero stores are ordered before lane 0's release
+    if (lane == 0) {
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      st_relaxed(done + t, 1);
+      red_relaxed_inc(blk_cnt + (t >> 5));
     }
   };
 
-  // A claimed tile starts its zero-fill at once (every later tile's scatter waits for it), but
-  // its segments are processed one tile later: by then the zero-fills of all earlier tiles,
-  // which were claimed before it, have long been published and the wait below is free.
-  if (tid == 0) s_tile[0] = atomicAdd(counter, 1);
-  __syncthreads();
-  int t = s_tile[0], cb = 0;
+  int t = claim(), cb = 0;
   if (t >= fa.ntiles) return;
-  phase0(t, 0);
+  produce(t, 0);
   for (;;) {
-    __syncthreads();  // everyone is done with the tile that lived in buffer cb ^ 1
-    if (tid == 0) {
-      s_tile[cb ^ 1] = atomicAdd(counter, 1);
-      s_cursor = 0;
-    }
-    __syncthreads();
-    const int t_next = s_tile[cb ^ 1];
-    if (t_next < fa.ntiles) phase0(t_next, cb ^ 1);
+    const int t_next = claim();
+    if (t_next < fa.ntiles) produce(t_next, cb ^ 1);
 
-    const int32_t *s_key = smem + cb * buf_ints, *s_slot = s_key + T + 1;
-    const float *s_scale = reinterpret_cast<const float *>(s_slot + T);
-    const int32_t *s_idx = reinterpret_cast<const int32_t *>(s_scale + T);
+    // every row tile t can touch was first-touched by a tile <= t: wait for all of them
+    wait_zero_fill(fa.ctrl, fa.nblk, t, lane, blk_wm);
+    const int32_t *s_key = wbuf + cb * kBufInts, *s_slot = s_key + 33;
+    const float *s_scale = reinterpret_cast<const float *>(s_slot + 32);
+    const int32_t *s_idx = s_key + kHdrInts;
+    const float *s_wout = reinterpret_cast<const float *>(s_idx + kIdxCap), *s_win = s_wout + kIdxCap;
     const int nseg = (int)min((int64_t)T, S - (int64_t)t * T);
     const int32_t p0 = s_key[0];
+    // per-row lookups: shared memory; global only for tiles that exceed the staging capacity
+    const bool staged = s_key[nseg] - p0 <= kIdxCap;   // warp-uniform
+    auto run_tile = [&](auto all_staged) {
+    constexpr bool kStaged = decltype(all_staged)::value;
+    auto row_idx = [&](int32_t p) -> uint32_t {
+      return (uint32_t)((kStaged || p - p0 < kIdxCap) ? s_idx[p - p0] : __ldg(fa.cflag + p));
+    };
+    auto row_win = [&](int32_t p, uint32_t v) -> float {
+      return (kStaged || p - p0 < kIdxCap) ? s_win[p - p0] : (a.a_in ? __ldg(a.a_in + v) : 1.0f);
+    };
+    auto row_wout = [&](int32_t p, uint32_t v) -> float {
+      return (kStaged || p - p0 < kIdxCap) ? s_wout[p - p0] : (a.a_out ? __ldg(a.a_out + v) : 1.0f);
+    };
 
-    // ---------------- phases 1 + 2: segments of the tile, one warp each ----------------
-    bool may_scatter = false;
-    for (;;) {
-      int i = 0;
-      if (lane == 0) i = atomicAdd(&s_cursor, 1);
-      i = __shfl_sync(kFull, i, 0);
-      if (i >= nseg) break;
-      const int32_t lo = s_key[i], hi = s_key[i + 1];
-      const int32_t slot = s_slot[i];
-      Acc<VPL> acc;
-      acc.zero();
-      for (int32_t base = lo; base < hi; base += 32) {
-        const int n = min(32, hi - base);
-        uint32_t my_c = 0;
-        float my_a = 1.0f;
-        if (lane < n) {
-          const int32_t p = base + lane;
-          my_c = (uint32_t)(p - p0 < kIdxCap ? s_idx[p - p0] : __ldg(fa.cflag + p));
-          if (a.a_in) my_a = __ldg(a.a_in + (my_c & kIdMask));
-        }
-#pragma unroll 4
-        for (int r0 = 0; r0 < n; r0 += groups) {
-          const int r = r0 + grp;
-          const uint32_t c = __shfl_sync(kFull, my_c, r & 31);
-          const float w = __shfl_sync(kFull, my_a, r & 31);
-          if (r < n) {
-            const float *xp = a.X + (int64_t)(c & kIdMask) * F + col;
+    // Split the tile's segments into kSub contiguous runs of about equal row count, one per
+    // sub-warp: the rows of a run are consecutive positions [plo, phi) of the index list.
+    int i_lo = 0, i_hi = nseg;
+    if (G::kSub > 1) {
+      const int32_t k_l = lane < nseg ? s_key[lane] : 0x7fffffff;
+      const int32_t rows = s_key[nseg] - p0;
 #pragma unroll
-            for (int j = 0; j < VPL; ++j) {
-              if (col + j * 128 < F) {
-                const float4 x = __ldg(reinterpret_cast<const float4 *>(xp + j * 128));
-                acc.v[j].x = fmaf(w, x.x, acc.v[j].x);
-                acc.v[j].y = fmaf(w, x.y, acc.v[j].y);
-                acc.v[j].z = fmaf(w, x.z, acc.v[j].z);
-                acc.v[j].w = fmaf(w, x.w, acc.v[j].w);
-              }
-            }
-          }
-        }
-      }
-      for (int off = lpr; off < 32; off <<= 1) {
-#pragma unroll
-        for (int j = 0; j < VPL; ++j) {
-          acc.v[j].x += __shfl_xor_sync(kFull, acc.v[j].x, off);
-          acc.v[j].y += __shfl_xor_sync(kFull, acc.v[j].y, off);
-          acc.v[j].z += __shfl_xor_sync(kFull, acc.v[j].z, off);
-          acc.v[j].w += __shfl_xor_sync(kFull, acc.v[j].w, off);
-        }
-      }
-      if (slot >= 0) {  // heavy hyperedge: publish the partial sum, pass 2 scatters
-        if (lane < lpr) {
-          float *sp = a.scratch + (int64_t)slot * F + col;
-#pragma unroll
-          for (int j = 0; j < VPL; ++j)
-            if (col + j * 128 < F) red_add_v4(sp + j * 128, acc.v[j]);
-        }
-        continue;
-      }
-      scale_acc<VPL>(acc, s_scale[i]);
-      if (!may_scatter) {  // every row this tile can touch was first-touched by a tile <= t
-        wait_zero_fill(fa.ctrl, fa.nblk, t, lane, blk_wm);
-        __syncwarp();
-        may_scatter = true;
-      }
-      for (int32_t base = lo; base < hi; base += 32) {
-        const int n = min(32, hi - base);
-        uint32_t my_c = 0;
-        float my_o = 1.0f;
-        if (lane < n) {
-          const int32_t p = base + lane;
-          my_c = (uint32_t)(p - p0 < kIdxCap ? s_idx[p - p0] : __ldg(fa.cflag + p));
-          if (a.a_out) my_o = __ldg(a.a_out + (my_c & kIdMask));
-        }
-#pragma unroll 4
-        for (int r0 = 0; r0 < n; r0 += groups) {
-          const int r = r0 + grp;
-          const uint32_t c = __shfl_sync(kFull, my_c, r & 31);
-          const float o = __shfl_sync(kFull, my_o, r & 31);
-          if (r < n) {
-            float *yp = a.Y + (int64_t)(c & kIdMask) * F + col;
-#pragma unroll
-            for (int j = 0; j < VPL; ++j) {
-              if (col + j * 128 < F) {
-                const float4 v = make_float4(acc.v[j].x * o, acc.v[j].y * o, acc.v[j].z * o, acc.v[j].w * o);
-                if (c & kExcl) st_v4(yp + j * 128, v);
-                else red_add_v4(yp + j * 128, v);
-              }
-            }
-          }
-        }
+      for (int g = 1; g < G::kSub; ++g) {
+        const int b = __popc(__ballot_sync(kFull, k_l < p0 + (int32_t)(((int64_t)rows * g) / G::kSub)));
+        if (g == sub) i_lo = b;
+        if (g == sub + 1) i_hi = b;
       }
     }
+    const int32_t plo = s_key[i_lo], phi = s_key[i_hi];
+    auto ring_slot = [&](int buf, int u, int j) {
+      return ring + ((((buf * G::kUnroll) + u) * VPL + j) * 32 + lane) * 4;
+    };
+    auto issue = [&](int buf, int32_t p) {
+#pragma unroll
+      for (int u = 0; u < G::kUnroll; ++u) {
+        if (p + u < phi) {
+          const float *xp = a.X + (int64_t)(row_idx(p + u) & kIdMask) * F + col;
+#pragma unroll
+          for (int j = 0; j < VPL; ++j)
+            if (col_ok<SW, VPL, EXACT>(col, j, F)) cp_async16(ring_slot(buf, u, j), xp + j * G::kColStride);
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int i = i_lo;
+    while (i < i_hi && s_key[i + 1] == s_key[i]) ++i;  // (empty segments carry no work)
+    int32_t seg_end = i < i_hi ? s_key[i + 1] : phi;
+    Acc<VPL> acc;
+    acc.zero();
+    int buf = 0;
+    issue(0, plo);
+    for (int32_t p = plo; p < phi; p += G::kUnroll) {
+      issue(buf ^ 1, p + G::kUnroll);              // (commits an empty group past the end)
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+#pragma unroll
+      for (int u = 0; u < G::kUnroll; ++u) {
+        if (p + u < phi) {
+          const float w = a.a_in ? row_win(p + u, row_idx(p + u) & kIdMask) : 1.0f;
+#pragma unroll
+          for (int j = 0; j < VPL; ++j) {
+            if (col_ok<SW, VPL, EXACT>(col, j, F)) {
+              const float4 x = *reinterpret_cast<const float4 *>(ring_slot(buf, u, j));
+              acc.v[j].x = fmaf(w, x.x, acc.v[j].x);
+              acc.v[j].y = fmaf(w, x.y, acc.v[j].y);
+              acc.v[j].z = fmaf(w, x.z, acc.v[j].z);
+              acc.v[j].w = fmaf(w, x.w, acc.v[j].w);
+            }
+          }
+          if (p + u + 1 == seg_end) {  // last member of segment i: finish it
+            const int32_t slot = s_slot[i];
+            if (slot >= 0) {           // heavy hyperedge: publish the partial sum, pass 2 scatters
+              float *sp = a.scratch + (int64_t)slot * F + col;
+#pragma unroll
+              for (int j = 0; j < VPL; ++j)
+                if (col_ok<SW, VPL, EXACT>(col, j, F)) red_add_v4(sp + j * G::kColStride, acc.v[j]);
+            } else {
+              scale_acc<VPL>(acc, s_scale[i]);
+#pragma unroll 2
+              for (int32_t q = s_key[i]; q < seg_end; ++q) {
+                const uint32_t c = row_idx(q);
+                const float o = row_wout(q, c & kIdMask);
+                float *yp = a.Y + (int64_t)(c & kIdMask) * F + col;
+                if (c & kExcl) {
+#pragma unroll
+                  for (int j = 0; j < VPL; ++j)
+                    if (col_ok<SW, VPL, EXACT>(col, j, F))
+                      st_v4(yp + j * G::kColStride, make_float4(acc.v[j].x * o, acc.v[j].y * o, acc.v[j].z * o,
+                                                                acc.v[j].w * o));
+                } else {
+#pragma unroll
+                  for (int j = 0; j < VPL; ++j)
+                    if (col_ok<SW, VPL, EXACT>(col, j, F))
+                      red_add_v4(yp + j * G::kColStride, make_float4(acc.v[j].x * o, acc.v[j].y * o,
+                                                                     acc.v[j].z * o, acc.v[j].w * o));
+                }
+              }
+            }
+            acc.zero();
+            ++i;
+            while (i < i_hi && s_key[i + 1] == s_key[i]) ++i;
+            seg_end = i < i_hi ? s_key[i + 1] : phi;
+          }
+        }
+      }
+      buf ^= 1;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    };  // run_tile
+    if (staged) run_tile(std::true_type{});
+    else run_tile(std::false_type{});
+    __syncwarp();  // all lanes are done with buffer cb before it is refilled
     if (t_next >= fa.ntiles) break;
     t = t_next;
     cb ^= 1;
@@ -288,15 +348,17 @@ __global__ void __launch_bounds__(kThreads) fused_kernel(const FusedArgs fa) {
 
 // Pass 2 for heavy hyperedges with the single-writer flags (rows that were never zero-filled
 // must be stored, not reduced).
-template <int VPL>
+template <int SW, int VPL>
 __global__ void __launch_bounds__(kThreads) fused_pass2_kernel(const FusedArgs fa) {
+  using G = Geo<SW, VPL>;
   const Args &a = fa.a;
   const int lane = threadIdx.x & 31;
-  const int lpr = a.lpr, groups = 32 / lpr, grp = lane / lpr;
-  const int col = (lane & (lpr - 1)) * 4;
+  const int sub = lane / SW;
+  const int col = (lane % SW) * 4;
   const int F = a.F;
-  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
-  for (int64_t i = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); i < a.nwork; i += nwarps) {
+  const int64_t nsub = (int64_t)gridDim.x * kWarpsPerBlock * G::kSub;
+  for (int64_t i = ((int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5)) * G::kSub + sub; i < a.nwork;
+       i += nsub) {
     const int32_t s = __ldg(a.seg_list + i);
     const int32_t lo = __ldg(a.key + s), hi = __ldg(a.key + s + 1);
     const float *sp = a.scratch + (int64_t)__ldg(a.seg_slot + s) * F + col;
@@ -305,73 +367,66 @@ __global__ void __launch_bounds__(kThreads) fused_pass2_kernel(const FusedArgs f
 #pragma unroll
     for (int j = 0; j < VPL; ++j) {
       acc.v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (col + j * 128 < F) acc.v[j] = *reinterpret_cast<const float4 *>(sp + j * 128);
+      if (col + j * G::kColStride < F) acc.v[j] = *reinterpret_cast<const float4 *>(sp + j * G::kColStride);
     }
     scale_acc<VPL>(acc, sc);
-    for (int32_t base = lo; base < hi; base += 32) {
-      const int n = min(32, hi - base);
-      uint32_t my_c = 0;
-      float my_o = 1.0f;
-      if (lane < n) {
-        my_c = (uint32_t)__ldg(fa.cflag + base + lane);
-        if (a.a_out) my_o = __ldg(a.a_out + (my_c & kIdMask));
-      }
 #pragma unroll 4
-      for (int r0 = 0; r0 < n; r0 += groups) {
-        const int r = r0 + grp;
-        const uint32_t c = __shfl_sync(kFull, my_c, r & 31);
-        const float o = __shfl_sync(kFull, my_o, r & 31);
-        if (r < n) {
-          float *yp = a.Y + (int64_t)(c & kIdMask) * F + col;
+    for (int32_t p = lo; p < hi; ++p) {
+      const uint32_t c = (uint32_t)__ldg(fa.cflag + p);
+      const uint32_t v = c & kIdMask;
+      const float o = a.a_out ? __ldg(a.a_out + v) : 1.0f;
+      float *yp = a.Y + (int64_t)v * F + col;
 #pragma unroll
-          for (int j = 0; j < VPL; ++j) {
-            if (col + j * 128 < F) {
-              const float4 v = make_float4(acc.v[j].x * o, acc.v[j].y * o, acc.v[j].z * o, acc.v[j].w * o);
-              if (c & kExcl) st_v4(yp + j * 128, v);
-              else red_add_v4(yp + j * 128, v);
-            }
-          }
+      for (int j = 0; j < VPL; ++j) {
+        if (col + j * G::kColStride < F) {
+          const float4 val = make_float4(acc.v[j].x * o, acc.v[j].y * o, acc.v[j].z * o, acc.v[j].w * o);
+          if (c & kExcl) st_v4(yp + j * G::kColStride, val);
+          else red_add_v4(yp + j * G::kColStride, val);
         }
       }
     }
   }
 }
 
-template <int VPL>
+template <int SW, int VPL, bool EXACT>
 int launch(hgPlan *plan, FusedArgs &fa, cudaStream_t s) {
+  using G = Geo<SW, VPL>;
   const int F = fa.a.F;
-  // tile size: the tiles in flight (2 per resident CTA) plus the rows still waiting for their
-  // last reduction must stay L2-resident, so tiles are small: ~64 KB of gathered + scattered rows
+  // warp-tile size: ~tile_kb of gathered + scattered rows, a multiple of the row streams of a warp,
+  // at most one staging lane per segment (31) and, on average, within the staging capacity
   const double avg_len = (double)plan->nnz / (double)plan->nseg;
-  static const double tile_kb = getenv("HGEF_TILE_KB") ? atof(getenv("HGEF_TILE_KB")) : 64.0;
+  static const double tile_env = getenv("HGEF_TILE_KB") ? atof(getenv("HGEF_TILE_KB")) : 0.0;
+  const double tile_kb = tile_env > 0 ? tile_env : (F >= 128 ? 128.0 : 64.0);
   int T = (int)(tile_kb * 1024.0 / (avg_len * 4.0 * F * 2.0));
-  T = T < 8 ? 8 : (T > 512 ? 512 : T);
-  T = (T + 7) & ~7;
+  const int cap_T = (int)(0.75 * kIdxCap / avg_len);
+  if (T > cap_T) T = cap_T;
+  T = T / G::kSub * G::kSub;
+  if (T > 31) T = 31 / G::kSub * G::kSub;
+  if (T < G::kSub) T = G::kSub;
   fa.tile_segs = T;
   fa.ntiles = (int32_t)ceil_div<int64_t>(plan->nseg, T);
-  const size_t smem = (size_t)2 * (3 * T + 1 + kIdxCap) * sizeof(int32_t);
-  static bool attr_set[8] = {};
-  if (!attr_set[VPL]) {
-    HG_CUDA_TRY(cudaFuncSetAttribute(fused_kernel<VPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    attr_set[VPL] = true;
-  }
+  fa.nblk = (fa.ntiles + 31) / 32;
+  const size_t smem = (size_t)kWarpsPerBlock * 2 * kBufInts * sizeof(int32_t) +
+                      (size_t)kWarpsPerBlock * 2 * G::kUnroll * VPL * 32 * sizeof(float4);
+  HG_CUDA_TRY(cudaFuncSetAttribute(fused_kernel<SW, VPL, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   128 * 1024));
   int per_sm = 0;
-  HG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_kernel<VPL>, kThreads, smem));
+  HG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_kernel<SW, VPL, EXACT>, kThreads, smem));
   if (per_sm < 1) per_sm = 1;
   int64_t grid = (int64_t)plan->sm_count * per_sm;
-  if (grid > fa.ntiles) grid = fa.ntiles;
-  fa.nblk = (fa.ntiles + 31) / 32;
+  const int64_t max_useful = ceil_div<int64_t>(fa.ntiles, kWarpsPerBlock);
+  if (grid > max_useful) grid = max_useful;
   HG_CUDA_TRY(cudaMemsetAsync(plan->ctrl, 0, (size_t)(fa.ntiles + fa.nblk + 8) * sizeof(int32_t), s));
   fa.ctrl = plan->ctrl;
   fa.a.nwork = plan->nseg;
-  fused_kernel<VPL><<<(unsigned)grid, kThreads, smem, s>>>(fa);
+  fused_kernel<SW, VPL, EXACT><<<(unsigned)grid, kThreads, smem, s>>>(fa);
   HG_CUDA_TRY(cudaGetLastError());
   if (plan->nheavy_segs > 0) {
     fa.a.nwork = plan->nheavy_segs;
     fa.a.seg_list = plan->heavy_segs;
-    int64_t g2 = ceil_div<int64_t>(plan->nheavy_segs, kWarpsPerBlock);
+    int64_t g2 = ceil_div<int64_t>(plan->nheavy_segs, kWarpsPerBlock * G::kSub);
     if (g2 > (int64_t)plan->sm_count * 8) g2 = (int64_t)plan->sm_count * 8;
-    fused_pass2_kernel<VPL><<<(unsigned)g2, kThreads, 0, s>>>(fa);
+    fused_pass2_kernel<SW, VPL><<<(unsigned)g2, kThreads, 0, s>>>(fa);
     HG_CUDA_TRY(cudaGetLastError());
   }
   return HG_OK;
@@ -390,7 +445,15 @@ int fused_check(hgPlan *plan, cudaStream_t s) {
   return HG_OK;
 }
 
-bool fused_available(const hgPlan *plan) { return plan->cflag != nullptr && plan->ctrl != nullptr; }
+// The persistent form pays off when segments are short (its per-warp staging holds kIdxCap rows;
+// with ngs-long segments, e.g. the Walmart-shaped graph, the two-pass kernel's 32-wide index
+// batches are the better fit -- measured 1.6 ms vs 3.1 ms at F=32).
+bool fused_available(const hgPlan *plan) {
+  if (plan->cflag == nullptr || plan->ctrl == nullptr) return false;
+  static const int force = getenv("HGEF_FORCE_FUSED") ? atoi(getenv("HGEF_FORCE_FUSED")) : 0;
+  if (force) return true;
+  return (double)plan->nnz / (double)plan->nseg <= 0.25 * kIdxCap;
+}
 
 // Y is NOT zero-filled by the caller; scratch (if any) is.
 int launch_fused(hgPlan *plan, const dev::Args &base, cudaStream_t s) {
@@ -399,9 +462,24 @@ int launch_fused(hgPlan *plan, const dev::Args &base, cudaStream_t s) {
   fa.cflag = plan->cflag;
   fa.iso = plan->iso_list;
   fa.niso = plan->niso;
-  if (base.F <= 128) return launch<1>(plan, fa, s);
-  if (base.F <= 256) return launch<2>(plan, fa, s);
-  return launch<4>(plan, fa, s);
+  const int F = base.F;
+  // sub-warp width: a whole warp per row from F = 128 up (no divergence between row streams),
+  // narrower sub-warps below so that all 32 lanes still carry data
+  static const int sw_env = getenv("HGEF_SW") ? atoi(getenv("HGEF_SW")) : 0;
+  int sw = sw_env;
+  if (sw != 4 && sw != 8 && sw != 16 && sw != 32) sw = F <= 16 ? 4 : (F <= 64 ? 8 : (F <= 128 ? 16 : 32));
+  while (sw < 32 && F > sw * 16) sw *= 2;  // at most 4 vectors per lane
+  const int vpl = F <= sw * 4 ? 1 : (F <= sw * 8 ? 2 : 4);
+  const bool exact = F == sw * 4 * vpl;
+#define HG_CASE(SW_, VPL_)                                               \
+  if (sw == SW_ && vpl == VPL_)                                          \
+    return exact ? launch<SW_, VPL_, true>(plan, fa, s) : launch<SW_, VPL_, false>(plan, fa, s)
+  HG_CASE(4, 1); HG_CASE(4, 2); HG_CASE(4, 4);
+  HG_CASE(8, 1); HG_CASE(8, 2); HG_CASE(8, 4);
+  HG_CASE(16, 1); HG_CASE(16, 2); HG_CASE(16, 4);
+  HG_CASE(32, 1); HG_CASE(32, 2); HG_CASE(32, 4);
+#undef HG_CASE
+  return set_error(HG_EINVAL, "launch_fused: no kernel for F=%d", F);
 }
 
 }  // namespace hg

@@ -192,8 +192,9 @@ int build_fused(hgPlan *p, cudaStream_t s) {
   HG_CUDA_TRY(cudaMemsetAsync(cnt.p, 0, (size_t)N * sizeof(int32_t), s));
   HG_CUDA_TRY(cudaMemsetAsync(minpos.p, 0x7f, (size_t)N * sizeof(int32_t), s));
   HG_CUDA_TRY(cudaMalloc((void **)&p->cflag, (size_t)Z * sizeof(int32_t)));
-  HG_CUDA_TRY(cudaMalloc((void **)&p->ctrl, (size_t)(p->nseg + 64) * sizeof(int32_t)));
-  HG_CUDA_TRY(cudaMemsetAsync(p->ctrl, 0, (size_t)(p->nseg + 64) * sizeof(int32_t), s));
+  const size_t ctrl_ints = (size_t)p->nseg + (size_t)p->nseg / 32 + 64;  // tiles of >= 1 segment
+  HG_CUDA_TRY(cudaMalloc((void **)&p->ctrl, ctrl_ints * sizeof(int32_t)));
+  HG_CUDA_TRY(cudaMemsetAsync(p->ctrl, 0, ctrl_ints * sizeof(int32_t), s));
   vertex_touch_kernel<<<GRID(Z), 0, s>>>(Z, p->colind, cnt.p, minpos.p);
   cflag_kernel<<<GRID(Z), 0, s>>>(Z, p->colind, cnt.p, minpos.p, p->cflag);
   iso_flag_kernel<<<GRID(N), 0, s>>>(N, cnt.p, iso.p, excl.p);

@@ -12,10 +12,10 @@
 constexpr int F = 128;
 __device__ __forceinline__ uint32_t mix(uint32_t x) { x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16; return x; }
 
-enum { GATHER, STORE, ATOMIC, REDV4, BULKRED, BULKLD };
+enum { GATHER, STORE, ATOMIC, REDV4, BULKRED, BULKLD, MIXED };
 
 template <int MODE>
-__global__ void __launch_bounds__(256) k(float *buf, uint32_t nrows, uint32_t rows_per_warp, float *sink) {
+__global__ void __launch_bounds__(256) k(float *buf, uint32_t nrows, uint32_t rows_per_warp, float *sink, uint32_t nrows_y = 0, uint32_t ywin = 1) {
   extern __shared__ __align__(128) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t gw = blockIdx.x * 8 + warp;
@@ -54,6 +54,18 @@ __global__ void __launch_bounds__(256) k(float *buf, uint32_t nrows, uint32_t ro
 #pragma unroll
       for (int u = 0; u < 4; ++u)
         asm volatile("red.global.add.v4.f32 [%0], {%1,%1,%1,%1};" ::"l"(buf + (size_t)r[u] * F + lane * 4), "f"(1.0f) : "memory");
+    } else if (MODE == MIXED) {   // the aggregation's mix: gather 4 rows (whole buffer), reduce, red to 4 rows (first 1/4)
+      float4 sum = make_float4(0, 0, 0, 0);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float4 x = __ldg(reinterpret_cast<const float4 *>(buf + (size_t)r[u] * F) + lane);
+        sum.x += x.x; sum.y += x.y; sum.z += x.z; sum.w += x.w;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t y = nrows + (mix(r[u] ^ 0x9e3779b9u) % ywin);  // one window shared by all warps
+        asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(buf + (size_t)y * F + lane * 4), "f"(sum.x), "f"(sum.y), "f"(sum.z), "f"(sum.w) : "memory");
+      }
     } else if (MODE == BULKRED) {
       if (lane == 0) {
 #pragma unroll
@@ -114,6 +126,24 @@ int main() {
     run<ATOMIC>("atomic", buf, nrows, sink, ws);
     run<REDV4>("red.v4", buf, nrows, sink, ws);
     run<BULKRED>("bulk_red", buf, nrows, sink, ws);
+  }
+  // mixed: X = first 1 GB (DRAM-resident gathers); Y = second 1 GB, the reds of a warp land in a
+  // sliding window of `ywin` rows (L2-resident window, as in the fused kernel where Y rows are
+  // zero-filled just ahead of use)
+  {
+    const uint32_t nx = (uint32_t)((big / 2) / (F * 4)), ny = nx;
+    for (uint32_t ywin : {40000u, 160000u, 400000u, ny - 1}) {
+      const uint32_t rows_per_warp = 512, blocks = 148 * 8 * 4;
+      cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+      k<MIXED><<<blocks, 256>>>(buf, nx, rows_per_warp, sink, ny, ywin);
+      CK(cudaDeviceSynchronize());
+      cudaEventRecord(a);
+      for (int it = 0; it < 3; ++it) k<MIXED><<<blocks, 256>>>(buf, nx, rows_per_warp, sink, ny, ywin);
+      cudaEventRecord(b); CK(cudaDeviceSynchronize());
+      float ms; cudaEventElapsedTime(&ms, a, b); ms /= 3;
+      double bytes = (double)blocks * 8 * rows_per_warp * F * 4;
+      printf("mixed    ywin=%8u rows  %8.3f ms  gather %8.1f GB/s + red %8.1f GB/s\n", ywin, ms, bytes / ms / 1e6, bytes / ms / 1e6);
+    }
   }
   return 0;
 }

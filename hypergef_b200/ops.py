@@ -31,7 +31,7 @@ from . import _native
 
 __all__ = [
     "hgnnaggr", "hgnnaggr_mean", "hgnnaggr_max", "unignnaggrdeg", "unignnaggr",
-    "set_backward_mode", "get_backward_mode", "aggregate", "aggregate_host", "Plan", "get_plan", "clear_plan_cache",
+    "set_backward_mode", "get_backward_mode", "aggregate", "aggregate_host", "HostPipeline", "Plan", "get_plan", "clear_plan_cache",
     "launch_count",
 ]
 
@@ -199,26 +199,64 @@ def aggregate(plan: Plan, X, s1=None, s2=None, a_out=None, a_in=None, out=None, 
     return out
 
 
+class HostPipeline:
+    """Aggregation for HOST feature matrices (numpy / CPU torch callers), copies overlapped.
+
+    Three streams: host->device copies, the aggregation launches, device->host copies.  Calls
+    submitted back to back overlap -- the upload of call k+1 and the download of call k-1 run
+    while call k computes (PCIe is full duplex) -- and all launches share ONE compute stream, so
+    the plan's per-call scratch is never used by two launches at once.  ``wait()`` blocks until
+    every submitted result is in its host buffer.  Pinned host buffers make the copies real DMA.
+    """
+
+    def __init__(self, plan: Plan):
+        self.plan = plan
+        with torch.cuda.device(plan.device_index):
+            self.h2d, self.compute, self.d2h = (torch.cuda.Stream() for _ in range(3))
+        self._keep = []
+
+    def submit(self, X_host, out_host=None, s1=None, s2=None, a_out=None, a_in=None):
+        plan = self.plan
+        if not isinstance(X_host, torch.Tensor):
+            X_host = torch.as_tensor(X_host)
+        if X_host.is_cuda or X_host.dtype != torch.float32 or X_host.dim() != 2:
+            raise TypeError("aggregate_host needs a 2-D float32 CPU tensor")
+        X_host = X_host.contiguous()
+        if out_host is None:
+            out_host = torch.empty_like(X_host, pin_memory=X_host.is_pinned())
+        if out_host.shape != X_host.shape or out_host.dtype != torch.float32 or out_host.is_cuda \
+                or not out_host.is_contiguous():
+            raise ValueError("out_host must be a contiguous float32 CPU tensor of X_host's shape")
+        with torch.cuda.device(plan.device_index):
+            with torch.cuda.stream(self.h2d):
+                Xd = X_host.to(plan.device, non_blocking=True)
+                up = torch.cuda.Event()
+                up.record()
+            with torch.cuda.stream(self.compute):
+                self.compute.wait_event(up)
+                Yd = aggregate(plan, Xd, s1=s1, s2=s2, a_out=a_out, a_in=a_in)
+                Xd.record_stream(self.compute)
+                done = torch.cuda.Event()
+                done.record()
+            with torch.cuda.stream(self.d2h):
+                self.d2h.wait_event(done)
+                out_host.copy_(Yd, non_blocking=True)
+                Yd.record_stream(self.d2h)
+        self._keep.append((X_host, out_host))
+        return out_host
+
+    def wait(self):
+        self.d2h.synchronize()
+        self._keep.clear()
+
+
 def aggregate_host(plan: Plan, X_host, out_host=None, s1=None, s2=None, a_out=None, a_in=None):
-    """The same aggregation for HOST feature matrices (what a caller holding numpy / CPU torch
-    data uses): ``X_host`` [N,F] fp32 -> device, ``hg_aggr_forward``, result -> ``out_host``.
-    Pinned buffers make both copies asynchronous DMA; the graph and scales stay on the device."""
-    if not isinstance(X_host, torch.Tensor):
-        X_host = torch.as_tensor(X_host)
-    if X_host.is_cuda or X_host.dtype != torch.float32 or X_host.dim() != 2:
-        raise TypeError("aggregate_host needs a 2-D float32 CPU tensor")
-    X_host = X_host.contiguous()
-    if out_host is None:
-        out_host = torch.empty_like(X_host, pin_memory=X_host.is_pinned())
-    if out_host.shape != X_host.shape or out_host.dtype != torch.float32 or out_host.is_cuda \
-            or not out_host.is_contiguous():
-        raise ValueError("out_host must be a contiguous float32 CPU tensor of X_host's shape")
-    with torch.cuda.device(plan.device_index):
-        Xd = X_host.to(plan.device, non_blocking=True)
-        Yd = aggregate(plan, Xd, s1=s1, s2=s2, a_out=a_out, a_in=a_in)
-        out_host.copy_(Yd, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-    return out_host
+    """One blocking host-buffer aggregation: ``X_host`` [N,F] fp32 -> device -> ``hg_aggr_forward``
+    -> ``out_host``.  For several matrices use :class:`HostPipeline` so the copies overlap."""
+    pipe = HostPipeline(plan)
+    out = pipe.submit(X_host, out_host, s1=s1, s2=s2, a_out=a_out, a_in=a_in)
+    pipe.wait()
+    return out
 
 
 def _weight_grad(csrptr_t, indices_t, X, G, s1, a_out, a_in, M):

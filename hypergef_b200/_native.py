@@ -47,6 +47,8 @@ SIGNATURES = {
     "hg_aggr_forward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp],
     "hg_aggr_groups": [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32,
                        _int, _vp],
+    "hg_edge_reduce": [_i64, _vp, _vp, _vp, _vp, _vp, _i32, _int, _vp],
+    "hg_edge_scatter": [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _int, _vp],
     "hg_aggr_mean": [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _int, _vp],
     "hg_aggr_max_forward": [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _int, _vp],
     "hg_aggr_max_backward": [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _int, _vp],

@@ -145,6 +145,21 @@ HG_API int hg_aggr_groups(int64_t num_nodes, int64_t ngroup, const int32_t *d_ke
                           const float *d_s2, const float *d_a_out, const float *d_a_in,
                           float *d_Y, int32_t F, int32_t flags, int device, void *stream);
 
+/* ------------------------------------------------------------------------- *
+ * The two stages as separate launches, for the vertex/hyperedge-PARTITIONED multi-GPU path
+ * (new capability; the reference is single-GPU).  Rows of the CSR are the BOUNDARY hyperedges
+ * restricted to the caller's vertex block; interior hyperedges stay on hg_aggr_forward.
+ *   hg_edge_reduce   P[e,:]  = sum_{u in row e} a_in[u] * X[u,:]            (P is overwritten)
+ *   hg_edge_scatter  Y[v,:] += a_out[v] * scale[e] * Q[e,:]  for v in row e   (Y is accumulated)
+ * scale / a_in / a_out may be NULL (= 1).  Any F >= 1.
+ * ------------------------------------------------------------------------- */
+HG_API int hg_edge_reduce(int64_t nrow, const int32_t *d_indptr, const int32_t *d_indices,
+                          const float *d_X, const float *d_a_in, float *d_P, int32_t F, int device,
+                          void *stream);
+HG_API int hg_edge_scatter(int64_t nrow, const int32_t *d_indptr, const int32_t *d_indices,
+                           const float *d_Q, const float *d_scale, const float *d_a_out, float *d_Y,
+                           int32_t F, int device, void *stream);
+
 /* f1-mean / f1-max first-stage variants over the un-balanced CSR of H^T.
  * Replace hgnnaggr_mean_fp_cuda / _bp_cuda (hgnnaggr_cuda.cu:408-470) and
  * hgnnaggr_max_fp_cuda / _bp_cuda (:472-543).  The hyperedge loop is bounded by

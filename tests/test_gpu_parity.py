@@ -282,3 +282,53 @@ def test_errors_raise_instead_of_aborting(cuda_device):
     with pytest.raises(_native.HgefGraphError):
         ops.get_plan(badk, hg.group_row, hg.group_start, hg.group_end, hg.H_T_colind, hg.num_nodes, hg.num_edges)
     assert _native.lib().hg_device_cc(0) == 100             # B200 = sm_100
+
+
+# ------------------------------------------------------------------ partitioned (multi-GPU) building blocks
+@pytest.mark.parametrize("F", [7, 32, 256])
+def test_stage_kernels_and_two_rank_emulation(F, cuda_device):
+    """hg_edge_reduce / hg_edge_scatter against the oracle, then the whole partitioned algorithm for
+    two ranks emulated on one GPU (the exchange done by hand from the PartitionInfo lists; the real
+    all_to_all path is covered on CPU by tests/test_partition_cpu.py and on 2 GPUs by tools/run_partition.py)."""
+    from hypergef_b200.partition import CudaBackend, build_partition
+    d, hg = _graph("mini_rep3", cuda_device)
+    N, M = hg.num_nodes, hg.num_edges
+    gen = torch.Generator().manual_seed(F)
+    X0 = torch.randn(N, F, generator=gen)
+    W0 = 0.5 + torch.rand(M, generator=gen)
+    X, W = X0.to(cuda_device), W0.to(cuda_device)
+    be = CudaBackend(cuda_device, ngs=int(d["ngs"]))
+    # stage 1 + stage 2 over the full CSR == the fused operator
+    P = be.edge_reduce(hg.H_T_csrptr, hg.H_T_colind, X, None)
+    rows = np.repeat(np.arange(M), np.diff(d["H_T_csrptr"]))
+    wantP = np.zeros((M, F)); np.add.at(wantP, rows, X0.numpy().astype(np.float64)[d["H_T_colind"]])
+    assert orc.rel_err(_np(P), wantP) < TOL
+    Y = torch.zeros(N, F, device=cuda_device)
+    be.edge_scatter(hg.H_T_csrptr, hg.H_T_colind, P, (hg.degE.reshape(-1) * W).contiguous(), hg.degV.reshape(-1), Y)
+    want = orc.c_aggr_formula(d["H_T_csrptr"], d["H_T_colind"], X0, s1=d["degE"], s2=W0, a_out=d["degV"])
+    assert orc.rel_err(_np(Y), want) < TOL
+    # two ranks on one device
+    world = 2
+    infos = [build_partition(hg.H_T_csrptr, hg.H_T_colind, N, M, world, r) for r in range(world)]
+    assert infos[0].num_boundary_total > 0
+    s = (hg.degE.reshape(-1) * W)
+    degV = hg.degV.reshape(-1)
+    Ps = [be.edge_reduce(i.bnd_ptr, i.bnd_ind, X[i.v_start:i.v_end].contiguous(), None) for i in infos]
+    Qs = [p.clone() for p in Ps]
+    for r, a in enumerate(infos):                 # owners add the partial rows their peers send
+        for q, b in enumerate(infos):
+            if q != r:
+                Qs[r][a.own_rows[a.recv_own_pos[q]]] += Ps[q][b.send_rows[r]]
+    for r, a in enumerate(infos):                 # and send the completed rows back
+        for q, b in enumerate(infos):
+            if q != r:
+                Qs[r][a.send_rows[q]] = Qs[q][b.own_rows[b.recv_own_pos[r]]]
+    outs = []
+    for r, a in enumerate(infos):
+        Xl, dl = X[a.v_start:a.v_end].contiguous(), degV[a.v_start:a.v_end].contiguous()
+        plan = be.prepare_interior(a.int_ptr, a.int_ind, a.num_local, a.int_edges.numel())
+        Yl = torch.full((a.num_local, F), float("nan"), device=cuda_device)
+        be.interior(plan, Xl, hg.degE.reshape(-1)[a.int_edges].contiguous(), W[a.int_edges].contiguous(), dl, None, Yl)
+        be.edge_scatter(a.bnd_ptr, a.bnd_ind, Qs[r], s[a.bnd_edges].contiguous(), dl, Yl)
+        outs.append(Yl)
+    assert orc.rel_err(_np(torch.cat(outs)), want) < TOL

@@ -274,6 +274,8 @@ def run_ours(args, rank, world, local_rank):
                     "ms_per_step": e2e_ms, "steps": e2e_steps},
             "gpu_launches": calls * (2 if plan.nheavy_segs else 1),
             "clocks": clocks.summary()}
+    if world == 1 and not args.no_extras:
+        line["same_gpu_baselines"] = same_gpu_baselines(hg, plan, Xs, Ys, W, features, bytes_f, peak)
     if world == 1 and not args.no_cpu_baseline:
         step, b_cpu, dims = cpu_conv_workload(args.ref_replicas, features)
         sec = time_cpu(step, 2, 1)
@@ -283,6 +285,42 @@ def run_ours(args, rank, world, local_rank):
             "sample": f"pubmed-shaped x{args.ref_replicas} replicas (N={dims['N']}), same F sweep, 2 timed passes of "
                       "the pure-torch restatement of model/pygnn/hgnn.py:30-37 on the host cores"}
     print(json.dumps(line), flush=True)
+
+
+def same_gpu_baselines(hg, plan, Xs, Ys, W, features, bytes_f, peak):
+    """Reported next to the headline (north star): cuSPARSE's two unfused SpMM calls on the same B200
+    (torch.sparse CSR @ dense = cusparseSpMM; H^T then H, scales folded into the CSR values, as
+    include/spmm/spmm.cuh:22-77,701-709) and this repo's own two-pass form (cudaMemset + segment kernel)."""
+    from hypergef_b200 import _native, ops
+    N, M = hg.num_nodes, hg.num_edges
+    degE, degV = hg.degE.reshape(-1), hg.degV.reshape(-1)
+    rows_t = torch.repeat_interleave(torch.arange(M, device=W.device), (hg.H_T_csrptr[1:] - hg.H_T_csrptr[:-1]).long())
+    HT = torch.sparse_csr_tensor(hg.H_T_csrptr, hg.H_T_colind, (degE * W)[rows_t], size=(M, N))
+    rows = torch.repeat_interleave(torch.arange(N, device=W.device), (hg.H_csrptr[1:] - hg.H_csrptr[:-1]).long())
+    H = torch.sparse_csr_tensor(hg.H_csrptr, hg.H_colind, degV[rows], size=(N, M))
+
+    def timed(fn, iters=10):
+        for _ in range(3):
+            fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters * 1e3
+    out = []
+    for F in features:
+        X = Xs[F]
+        us_cs = timed(lambda: torch.sparse.mm(H, torch.sparse.mm(HT, X)))
+        us_2p = timed(lambda: ops.aggregate(plan, X, s1=hg.degE, s2=W, a_out=hg.degV, out=Ys[F], flags=_native.HG_TWO_PASS))
+        ref = torch.sparse.mm(H, torch.sparse.mm(HT, X))
+        ops.aggregate(plan, X, s1=hg.degE, s2=W, a_out=hg.degV, out=Ys[F])
+        err = ((Ys[F] - ref).abs().max() / ref.abs().max()).item()
+        out.append({"F": F, "cusparse_2xspmm_us": us_cs, "cusparse_algorithmic_GBps": bytes_f[F] / us_cs / 1e3,
+                    "two_pass_us": us_2p, "two_pass_algorithmic_GBps": bytes_f[F] / us_2p / 1e3,
+                    "max_rel_diff_fused_vs_cusparse": err})
+    return out
 
 
 def main():
@@ -296,6 +334,7 @@ def main():
     ap.add_argument("--features", type=lambda s: [int(x) for x in s.split(",")], default=list(FEATURES))
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the cuSPARSE / two-pass same-GPU baselines")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -132,17 +132,20 @@ int main() {
   // zero-filled just ahead of use)
   {
     const uint32_t nx = (uint32_t)((big / 2) / (F * 4)), ny = nx;
-    for (uint32_t ywin : {40000u, 160000u, 400000u, ny - 1}) {
+    CK(cudaFuncSetAttribute(k<MIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    for (int occ : {8, 4, 2, 1})   // resident CTAs per SM, forced with dynamic shared memory
+    for (uint32_t ywin : {40000u, 160000u, ny - 1}) {
       const uint32_t rows_per_warp = 512, blocks = 148 * 8 * 4;
+      const size_t pad = occ >= 8 ? 0 : (size_t)(220 * 1024 / occ - 2048);
       cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
-      k<MIXED><<<blocks, 256>>>(buf, nx, rows_per_warp, sink, ny, ywin);
+      k<MIXED><<<blocks, 256, pad>>>(buf, nx, rows_per_warp, sink, ny, ywin);
       CK(cudaDeviceSynchronize());
       cudaEventRecord(a);
-      for (int it = 0; it < 3; ++it) k<MIXED><<<blocks, 256>>>(buf, nx, rows_per_warp, sink, ny, ywin);
+      for (int it = 0; it < 3; ++it) k<MIXED><<<blocks, 256, pad>>>(buf, nx, rows_per_warp, sink, ny, ywin);
       cudaEventRecord(b); CK(cudaDeviceSynchronize());
       float ms; cudaEventElapsedTime(&ms, a, b); ms /= 3;
       double bytes = (double)blocks * 8 * rows_per_warp * F * 4;
-      printf("mixed    ywin=%8u rows  %8.3f ms  gather %8.1f GB/s + red %8.1f GB/s\n", ywin, ms, bytes / ms / 1e6, bytes / ms / 1e6);
+      printf("mixed occ=%d CTAs/SM ywin=%8u rows  %8.3f ms  gather %8.1f GB/s + red %8.1f GB/s\n", occ, ywin, ms, bytes / ms / 1e6, bytes / ms / 1e6);
     }
   }
   return 0;

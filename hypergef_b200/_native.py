@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhgef_b200.so")
+LIB_PATH = os.environ.get("HGEF_B200_LIB") or os.path.join(_HERE, "libhgef_b200.so")   # (override: A/B builds)
 
 HG_OK, HG_EINVAL, HG_ECUDA, HG_ENOMEM, HG_EEMPTY, HG_EGRAPH = range(6)
 HG_ACCUMULATE, HG_FORCE_SCALAR, HG_TWO_PASS = 1, 4, 8

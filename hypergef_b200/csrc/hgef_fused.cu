@@ -118,8 +118,8 @@ template <int SW, int VPL>
 struct Geo {
   static constexpr int kSub = 32 / SW;        // row streams per warp
   static constexpr int kColStride = SW * 4;   // floats between a lane's vectors
-  static constexpr int kUnroll = (SW * VPL >= 32 ? 8 : 4) / VPL;  // rows per pipeline step: 8 (rows >= 512 B)
-                                                               // or 4 x 16 B per lane in flight
+  static constexpr int kUnroll = (SW * VPL >= 64 ? 12 : (SW * VPL >= 32 ? 8 : 4)) / VPL;  // 16-byte vectors per lane and step:
+                                                               // 12 (rows >= 1 KB), 8 (>= 512 B), else 4
 };
 
 constexpr int kTileMax = 32;   // segments per warp tile (one staging lane per segment)

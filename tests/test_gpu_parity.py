@@ -332,3 +332,30 @@ def test_stage_kernels_and_two_rank_emulation(F, cuda_device):
         be.edge_scatter(a.bnd_ptr, a.bnd_ind, Qs[r], s[a.bnd_edges].contiguous(), dl, Yl)
         outs.append(Yl)
     assert orc.rel_err(_np(torch.cat(outs)), want) < TOL
+
+
+def test_addresses_beyond_int32(cuda_device):
+    """C5-shaped graph (window locality) at 1/10 scale with F=512: N*F = 2.56e9 > 2^31, the case the
+    reference's int32 address arithmetic (hgnnaggr_cuda.cu:34,44) cannot represent.  Checked by exact fp64
+    recomputation of sampled output rows (the full C5, N*F = 1.28e10, is tools/c5_single.py)."""
+    import dataclasses
+    shape = dataclasses.replace(synth.SHAPES["c5"], num_nodes=5_000_000, num_edges=1_000_000)
+    data = synth.make_shape("c5", seed=0, device=cuda_device, shape=shape)
+    hg = HyperGraph(data, cuda_device, "synthetic", ngs=shape.ngs)
+    del data
+    N, M, F = hg.num_nodes, hg.num_edges, 512
+    assert N * F > 2 ** 31
+    gen = torch.Generator(device=cuda_device).manual_seed(2)
+    X = torch.randn(N, F, device=cuda_device, generator=gen)
+    Y = hgef.HGNNAggr(hg, X, hg.degE, hg.degV, torch.ones(M, device=cuda_device))
+    degE, degV = hg.degE.reshape(-1).double(), hg.degV.reshape(-1).double()
+    Hp, Hc, Tp, Tc = hg.H_csrptr.long(), hg.H_colind.long(), hg.H_T_csrptr.long(), hg.H_T_colind.long()
+    sample = torch.cat([torch.randint(0, N, (64,), device=cuda_device, generator=gen),
+                        torch.tensor([0, N - 1, N - 2], device=cuda_device)])
+    for v in sample.tolist():
+        row = torch.zeros(F, dtype=torch.float64, device=cuda_device)
+        for e in Hc[Hp[v]:Hp[v + 1]].tolist():
+            row += degE[e] * X[Tc[Tp[e]:Tp[e + 1]]].double().sum(0)
+        row *= degV[v]
+        err = ((Y[v].double() - row).abs().max() / row.abs().max().clamp_min(1e-30)).item()
+        assert err < TOL, (v, err)

@@ -35,7 +35,7 @@ namespace {
 using namespace dev;
 
 constexpr uint32_t kFirst = 0x80000000u, kExcl = 0x40000000u, kIdMask = 0x3fffffffu;
-constexpr int kIdxCap = 96;  // staged rows per warp tile (index, a_out, a_in); beyond that: global reads
+constexpr int kIdxCap = 192;  // staged rows per warp tile (index, a_out, a_in); beyond that: global reads
 
 struct FusedArgs {
   Args a;
@@ -409,7 +409,7 @@ int launch(hgPlan *plan, FusedArgs &fa, cudaStream_t s) {
   const size_t smem = (size_t)kWarpsPerBlock * 2 * kBufInts * sizeof(int32_t) +
                       (size_t)kWarpsPerBlock * 2 * G::kUnroll * VPL * 32 * sizeof(float4);
   HG_CUDA_TRY(cudaFuncSetAttribute(fused_kernel<SW, VPL, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   128 * 1024));
+                                   227 * 1024));
   int per_sm = 0;
   HG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_kernel<SW, VPL, EXACT>, kThreads, smem));
   if (per_sm < 1) per_sm = 1;

@@ -187,12 +187,25 @@ __global__ void __launch_bounds__(kThreads) fused_kernel(const FusedArgs fa) {
       s_win[i] = a.a_in ? __ldg(a.a_in + (c & kIdMask)) : 1.0f;
     }
     __syncwarp();
-    for (int32_t pb = p0; pb < p1; pb += G::kSub) {
-      const int32_t p = pb + sub;
-      if (p < p1) {
-        const uint32_t c = (uint32_t)(p - p0 < kIdxCap ? s_idx[p - p0] : __ldg(fa.cflag + p));
-        if ((c & kFirst) && !(c & kExcl)) {
-          float *yp = a.Y + (int64_t)(c & kIdMask) * F + col;
+    // (32 rows' flags are tested at once; only the flagged rows -- about a third -- cost a store pass)
+    for (int32_t pb = p0; pb < p1; pb += 32) {
+      const int32_t p = pb + lane;
+      uint32_t c = 0;
+      if (p < p1) c = (uint32_t)(p - p0 < kIdxCap ? s_idx[p - p0] : __ldg(fa.cflag + p));
+      unsigned m = __ballot_sync(kFull, (c & kFirst) && !(c & kExcl));
+      while (m) {  // kSub flagged rows per pass, one per sub-warp
+        int b = -1;
+#pragma unroll
+        for (int g = 0; g < G::kSub; ++g) {
+          if (m) {
+            const int bit = __ffs(m) - 1;
+            m &= m - 1;
+            if (g == sub) b = bit;
+          }
+        }
+        const uint32_t cv = __shfl_sync(kFull, c, b < 0 ? 0 : b);
+        if (b >= 0) {
+          float *yp = a.Y + (int64_t)(cv & kIdMask) * F + col;
 #pragma unroll
           for (int j = 0; j < VPL; ++j)
             if (col_ok<SW, VPL, EXACT>(col, j, F)) st_zero_v4(yp + j * G::kColStride);
@@ -201,11 +214,19 @@ __global__ void __launch_bounds__(kThreads) fused_kernel(const FusedArgs fa) {
     }
     // ... and this tile's share of the vertices that no hyperedge touches
     const int64_t i0 = fa.niso * t / fa.ntiles, i1 = fa.niso * (t + 1) / fa.ntiles;
-    for (int64_t i = i0 + sub; i < i1; i += G::kSub) {
-      float *yp = a.Y + (int64_t)__ldg(fa.iso + i) * F + col;
+    for (int64_t ib = i0; ib < i1; ib += 32) {
+      const int n = (int)min((int64_t)32, i1 - ib);
+      const int32_t my_v = lane < n ? __ldg(fa.iso + ib + lane) : 0;
+      for (int r0 = 0; r0 < n; r0 += G::kSub) {
+        const int r = r0 + sub;
+        const int32_t v = __shfl_sync(kFull, my_v, r & 31);
+        if (r < n) {
+          float *yp = a.Y + (int64_t)v * F + col;
 #pragma unroll
-      for (int j = 0; j < VPL; ++j)
-        if (col_ok<SW, VPL, EXACT>(col, j, F)) st_zero_v4(yp + j * G::kColStride);
+          for (int j = 0; j < VPL; ++j)
+            if (col_ok<SW, VPL, EXACT>(col, j, F)) st_zero_v4(yp + j * G::kColStride);
+        }
+      }
     }
     __syncwarp();  // the lanes' zero stores are ordered before lane 0's release
     if (lane == 0) {

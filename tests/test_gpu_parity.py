@@ -359,3 +359,24 @@ def test_addresses_beyond_int32(cuda_device):
         row *= degV[v]
         err = ((Y[v].double() - row).abs().max() / row.abs().max().clamp_min(1e-30)).item()
         assert err < TOL, (v, err)
+
+
+def test_host_pipeline_matches_device_path(cuda_device):
+    """The host-buffer API (pinned upload / launch / download overlapped over three streams)."""
+    d, hg = _graph("mini_rep3", cuda_device)
+    plan = ops.get_plan(hg.group_key, hg.group_row, hg.group_start, hg.group_end, hg.H_T_colind,
+                        hg.num_nodes, hg.num_edges)
+    pipe = ops.HostPipeline(plan)
+    outs, wants = [], []
+    for F in (8, 32, 128):
+        X = torch.randn(hg.num_nodes, F, generator=torch.Generator().manual_seed(F)).pin_memory()
+        outs.append(pipe.submit(X, None, s1=hg.degE, a_out=hg.degV))
+        wants.append(orc.c_aggr_formula(d["H_T_csrptr"], d["H_T_colind"], X, s1=d["degE"], a_out=d["degV"]))
+    pipe.wait()
+    for o, w in zip(outs, wants):
+        assert not o.is_cuda and orc.rel_err(o.numpy(), w) < TOL
+    X = torch.randn(hg.num_nodes, 16)
+    assert orc.rel_err(ops.aggregate_host(plan, X, s1=hg.degE, a_out=hg.degV).numpy(),
+                       orc.c_aggr_formula(d["H_T_csrptr"], d["H_T_colind"], X, s1=d["degE"], a_out=d["degV"])) < TOL
+    with pytest.raises(TypeError):
+        ops.aggregate_host(plan, X.cuda())

@@ -21,7 +21,7 @@
 #include "hgef_aggr.cuh"
 
 namespace hg {
-bool fused_available(const hgPlan *plan);
+bool fused_available(const hgPlan *plan, int F, bool force);
 int launch_fused(hgPlan *plan, const dev::Args &base, cudaStream_t s);
 int fused_check(hgPlan *plan, cudaStream_t s);
 namespace {
@@ -223,7 +223,7 @@ int hg_aggr_forward(hgPlan *plan, const float *d_X, const float *d_s1, const flo
   cudaStream_t s = (cudaStream_t)stream;
   const bool vec = F % 4 == 0 && F <= 512 && !(flags & HG_FORCE_SCALAR) && aligned16(d_X) && aligned16(d_Y);
   // single-launch persistent form: zero-fill happens inside the kernel (hgef_fused.cu)
-  const bool fused = vec && !(flags & (HG_ACCUMULATE | HG_TWO_PASS)) && fused_available(plan);
+  const bool fused = vec && !(flags & (HG_ACCUMULATE | HG_TWO_PASS)) && fused_available(plan, F, (flags & HG_FORCE_FUSED) != 0);
   if (!fused && !(flags & HG_ACCUMULATE))
     HG_CUDA_TRY(cudaMemsetAsync(d_Y, 0, (size_t)plan->num_nodes * F * sizeof(float), s));
   const bool heavy = plan->nheavy_segs > 0;

@@ -471,14 +471,17 @@ int fused_check(hgPlan *plan, cudaStream_t s) {
   return HG_OK;
 }
 
-// The persistent form pays off when segments are short (its per-warp staging holds kIdxCap rows;
-// with ngs-long segments, e.g. the Walmart-shaped graph, the two-pass kernel's 32-wide index
-// batches are the better fit -- measured 1.6 ms vs 3.1 ms at F=32).
-bool fused_available(const hgPlan *plan) {
+// When to use the persistent form (measured, profiles/r01_tuning_sweeps.txt):
+//  * Y must not fit the L2: below ~64 MB the memset and the reductions of the two-pass form never
+//    leave the L2 and its one-warp-per-segment grid has the lower latency (literal Pubmed, F=128:
+//    18 us vs 43 us; the crossover is at N*F*4 ~ 64 MB);
+//  * segments must be short: the per-warp staging holds kIdxCap rows; with ngs-long segments (the
+//    Walmart-shaped graph) the two-pass kernel's 32-wide index batches fit better (1.6 vs 3.1 ms).
+bool fused_available(const hgPlan *plan, int F, bool force) {
   if (plan->cflag == nullptr || plan->ctrl == nullptr) return false;
-  static const int force = getenv("HGEF_FORCE_FUSED") ? atoi(getenv("HGEF_FORCE_FUSED")) : 0;
   if (force) return true;
-  return (double)plan->nnz / (double)plan->nseg <= 0.25 * kIdxCap;
+  if ((double)plan->num_nodes * F * 4.0 < 64.0 * 1048576.0) return false;
+  return (double)plan->nnz / (double)plan->nseg <= 0.125 * kIdxCap;
 }
 
 // Y is NOT zero-filled by the caller; scratch (if any) is.

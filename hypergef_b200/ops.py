@@ -35,6 +35,7 @@ __all__ = [
     "launch_count",
 ]
 
+DEFAULT_FLAGS = 0       # OR-ed into every hg_aggr_forward call (tests force one kernel form with it)
 _BACKWARD_MODE = "transpose"
 _LAUNCHES = 0           # C-ABI aggregation calls issued (bench.py reports it)
 
@@ -194,7 +195,7 @@ def aggregate(plan: Plan, X, s1=None, s2=None, a_out=None, a_in=None, out=None, 
         return out.zero_() if not (flags & _native.HG_ACCUMULATE) else out
     stream = torch.cuda.current_stream(plan.device_index).cuda_stream
     _native.call("hg_aggr_forward", plan.handle, X.data_ptr(), _ptr(s1), _ptr(s2), _ptr(a_out),
-                 _ptr(a_in), out.data_ptr(), F, flags, stream)
+                 _ptr(a_in), out.data_ptr(), F, flags | DEFAULT_FLAGS, stream)
     _LAUNCHES += 1
     return out
 

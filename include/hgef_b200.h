@@ -116,7 +116,8 @@ HG_API int hg_plan_check(hgPlan *plan, void *stream);
 enum {
   HG_ACCUMULATE = 1,     /* do not zero-fill Y first (reference: torch::zeros, hgnnaggr_cuda.cu:374) */
   HG_FORCE_SCALAR = 4,   /* disable the 128-bit path (testing) */
-  HG_TWO_PASS = 8        /* memset + segment kernel instead of the single persistent launch (ablation) */
+  HG_TWO_PASS = 8,       /* always memset + segment kernels (the form chosen for small / long-segment graphs) */
+  HG_FORCE_FUSED = 16    /* always the single persistent launch (the form chosen when Y exceeds the L2) */
 };
 
 /* ------------------------------------------------------------------------- *

@@ -19,6 +19,15 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-5
 
 
+@pytest.fixture(params=["auto", "fused", "two_pass"])
+def kernel_form(request):
+    """Run a test with the library's own choice of kernel form, then with each form forced
+    (the persistent kernel is only chosen on its own when Y exceeds the L2)."""
+    ops.DEFAULT_FLAGS = {"auto": 0, "fused": _native.HG_FORCE_FUSED, "two_pass": _native.HG_TWO_PASS}[request.param]
+    yield request.param
+    ops.DEFAULT_FLAGS = 0
+
+
 def _graph(g, dev):
     d = load_golden("graph_" + g)
     data = SimpleNamespace(x=torch.zeros(int(d["num_nodes"]), 1), edge_index=torch.from_numpy(d["edge_index"]))
@@ -84,7 +93,7 @@ def test_device_csr_random_unsorted_duplicates(cuda_device):
 
 # ------------------------------------------------------------------ features: <= 1e-5 relative
 @pytest.mark.parametrize("g", ["mini", "mini_rep3"])
-def test_forward_matches_golden(g, cuda_device):
+def test_forward_matches_golden(g, cuda_device, kernel_form):
     d, hg = _graph(g, cuda_device)
     X = torch.from_numpy(d["X"]).to(cuda_device)
     W = torch.from_numpy(d["W"]).to(cuda_device)
@@ -100,7 +109,7 @@ def test_forward_matches_golden(g, cuda_device):
 
 
 @pytest.mark.parametrize("F", [1, 2, 7, 12, 32, 64, 100, 128, 200, 256, 512, 516])
-def test_forward_feature_lengths(F, cuda_device):
+def test_forward_feature_lengths(F, cuda_device, kernel_form):
     """Every vector layout (lanes/row 1..32, 1/2/4 vectors per lane) and the scalar tail path."""
     d, hg = _graph("mini", cuda_device)           # ngs=6, max hyperedge 75: light and heavy hyperedges
     N, M = hg.num_nodes, hg.num_edges
@@ -136,7 +145,7 @@ def test_plan_sees_heavy_hyperedges_and_schedules_agree(cuda_device):
     want = orc.c_aggr_groups(d["group_key"], d["group_row"], d["group_start"], d["group_end"], d["H_T_colind"],
                              d["X"], s1=d["degE"], a_out=d["degV"])
     assert orc.rel_err(_np(Y1), want) < TOL and orc.rel_err(_np(Y2), want) < TOL
-    for flag in (_native.HG_FORCE_SCALAR, _native.HG_TWO_PASS):     # scalar tail path; memset + 2-pass form
+    for flag in (_native.HG_FORCE_SCALAR, _native.HG_TWO_PASS, _native.HG_FORCE_FUSED):   # scalar tail; both kernel forms
         Y3 = ops.aggregate(plan, X, s1=hg.degE, a_out=hg.degV, flags=flag)
         assert orc.rel_err(_np(Y3), want) < TOL
     plan.check()
@@ -161,7 +170,7 @@ def test_non_canonical_groups_keep_reference_meaning(cuda_device):
     assert orc.rel_err(_np(Y), want) < TOL
 
 
-def test_backward_transpose_and_reference_modes(cuda_device):
+def test_backward_transpose_and_reference_modes(cuda_device, kernel_form):
     d, hg = _graph("mini", cuda_device)
     N, M = hg.num_nodes, hg.num_edges
     F = 16
@@ -221,7 +230,7 @@ def test_mean_and_max_variants(cuda_device):
 
 
 @pytest.mark.parametrize("shape,F", [("cora", 32), ("pubmed", 64), ("dblp", 128), ("walmart", 32)])
-def test_baseline_shapes_against_oracle(shape, F, cuda_device):
+def test_baseline_shapes_against_oracle(shape, F, cuda_device, kernel_form):
     """BASELINE.json configs at their literal sizes (C1-C4); walmart plants a 12345-member hyperedge."""
     data = synth.make_shape(shape, seed=0)
     hg = HyperGraph(data, cuda_device, data.dataset)
@@ -236,7 +245,7 @@ def test_baseline_shapes_against_oracle(shape, F, cuda_device):
     assert np.array_equal(_np(hg.group_key), b.balan_key) and np.array_equal(_np(hg.group_end), b.group_ed)
 
 
-def test_full_size_properties(cuda_device):
+def test_full_size_properties(cuda_device, kernel_form):
     """Pubmed-shaped x64 (the bench workload) at F=128: properties that need no CPU oracle --
     linearity, the adjoint identity <A x, z> = <x, A^T z>, and the column checksum
     1^T (H H^T X) = sum_e |e| (H^T X)_e."""
@@ -380,3 +389,37 @@ def test_host_pipeline_matches_device_path(cuda_device):
                        orc.c_aggr_formula(d["H_T_csrptr"], d["H_T_colind"], X, s1=d["degE"], a_out=d["degV"])) < TOL
     with pytest.raises(TypeError):
         ops.aggregate_host(plan, X.cuda())
+
+
+def test_ragged_and_degenerate_graphs(cuda_device):
+    """Edge cases: single-member hyperedges, isolated vertices (degV inf -> 1), a hyperedge holding every
+    vertex, one-hyperedge and one-vertex graphs, ngs = 1 (every member its own segment: w = deg, w^2 groups)."""
+    def build(members, N, ngs):
+        V = torch.tensor([v for e, ms in enumerate(members) for v in ms])
+        E = torch.tensor([e for e, ms in enumerate(members) for _ in ms])
+        order = torch.argsort(V * len(members) + E)
+        data = SimpleNamespace(x=torch.zeros(N, 1), edge_index=synth.incidence_to_edge_index(V[order], E[order], N))
+        return HyperGraph(data, cuda_device, "synthetic", ngs=ngs)
+    cases = [
+        ([[0], [3], [1, 2, 3], [5]], 8, 2),                    # singletons + isolated vertices 4, 6, 7
+        ([list(range(40))], 40, 7),                            # one hyperedge with every vertex, 6 segments
+        ([[0]], 1, 3),                                         # 1 x 1
+        ([[0, 1, 2, 3, 4], [2, 3], [4, 0]], 5, 1),             # ngs = 1
+        ([list(range(i, i + 3)) for i in range(0, 60, 3)] + [list(range(0, 60, 2))], 64, 4),
+    ]
+    for members, N, ngs in cases:
+        hg = build(members, N, ngs)
+        ptr, ind = _np(hg.H_T_csrptr), _np(hg.H_T_colind)
+        b = orc.c_balancer(ngs, ptr)
+        assert np.array_equal(_np(hg.group_key), b.balan_key) and np.array_equal(_np(hg.group_row), b.balan_row)
+        assert np.array_equal(_np(hg.group_start), b.group_st) and np.array_equal(_np(hg.group_end), b.group_ed)
+        assert torch.isfinite(hg.degV).all()
+        for F in (4, 5, 32):
+            X = torch.randn(N, F, generator=torch.Generator().manual_seed(N + F))
+            want = orc.c_aggr_formula(ptr, ind, X, s1=_np(hg.degE), a_out=_np(hg.degV))
+            out = torch.full((N, F), float("nan"), device=cuda_device)
+            plan = ops.get_plan(hg.group_key, hg.group_row, hg.group_start, hg.group_end, hg.H_T_colind, N, hg.num_edges)
+            for flags in (0, _native.HG_TWO_PASS, _native.HG_FORCE_FUSED):
+                ops.aggregate(plan, X.to(cuda_device), s1=hg.degE, a_out=hg.degV, out=out, flags=flags)
+                assert orc.rel_err(_np(out), want) < TOL or np.abs(want).max() == 0, (len(members), N, ngs, F, flags)
+            plan.check()

@@ -367,6 +367,276 @@ __global__ void __launch_bounds__(kThreads) fused_kernel(const FusedArgs fa) {
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Producer / consumer form.  The warp-autonomous kernel above keeps (#warps x 2) tiles in flight,
+// hundreds of MB of rows between zero-fill and last reduction, so at F >= 128 about half of the Y
+// rows are evicted and re-fetched (DRAM traffic 1.4-1.8x algorithmic, profiles/traffic.json), and
+// every warp pays the serial claim -> stage -> fence -> publish chain itself.  Here a CTA owns a
+// few LARGE tiles at a time:
+//   PRODUCER warps (NP of NW) claim tiles in order, stage them in shared memory (segment bounds,
+//     flagged indices, a_in / a_out per member), zero-fill the rows the tile touches first, fence,
+//     publish, wait until every earlier tile is published, and hand the tile to the consumers
+//     through an mbarrier.  They never have reductions in flight, so their fence is cheap.
+//   CONSUMER warps take runs of segments of the current tile from a shared cursor and stream
+//     them through their private cp.async ring exactly as above; they never touch global
+//     synchronisation state and never fence.
+// Tiles in flight: (#CTAs x NB) instead of (#warps x 2).
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const uint32_t addr = smem_u32(bar);
+  while (!ok)
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+}
+
+constexpr int kPcSegs = 128;   // max segments per CTA tile
+constexpr int kPcRows = 640;   // staged rows per CTA tile (beyond that: global reads)
+constexpr int kPcBufInts = (kPcSegs + 1 + 3) / 4 * 4 + 2 * kPcSegs + 3 * kPcRows;  // key | slot scale | idx wout win
+constexpr int kPcRun = 4;      // segments a consumer warp takes from the cursor at a time (x row streams)
+
+template <int SW, int VPL, bool EXACT, int NW, int NP, int NB>
+__global__ void __launch_bounds__(NW * 32) pc_kernel(const FusedArgs fa) {
+  using G = Geo<SW, VPL>;
+  constexpr int NC = NW - NP;
+  extern __shared__ __align__(16) int32_t smem[];
+  __shared__ __align__(8) uint64_t s_full[NB], s_empty[NB];
+  __shared__ int s_tile[NB], s_cursor[NB];
+  const Args &a = fa.a;
+  const int T = fa.tile_segs;                      // <= kPcSegs
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int sub = lane / SW;
+  const int col = (lane % SW) * 4;
+  const int F = EXACT ? SW * 4 * VPL : a.F;
+  const int64_t S = a.nwork;
+  if (tid == 0)
+    for (int b = 0; b < NB; ++b) { mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], NC); }
+  __syncthreads();
+  auto buf_key = [&](int b) { return smem + b * kPcBufInts; };
+
+  if (warp < NP) {
+    // ------------------------------ producer ------------------------------
+    int *counter = fa.ctrl, *blk_cnt = fa.ctrl + 8, *done = fa.ctrl + 8 + fa.nblk;
+    int blk_wm = 0;
+    for (int it = warp;; it += NP) {
+      const int b = it % NB;
+      if (it >= NB) mbar_wait(&s_empty[b], ((it / NB) - 1) & 1);
+      int t = 0;
+      if (lane == 0) t = atomicAdd(counter, 1);
+      t = __shfl_sync(kFull, t, 0);
+      if (t >= fa.ntiles) {
+        if (lane == 0) { s_tile[b] = -1; mbar_arrive(&s_full[b]); }
+        break;
+      }
+      int32_t *s_key = buf_key(b), *s_slot = s_key + (kPcSegs + 1 + 3) / 4 * 4;
+      float *s_scale = reinterpret_cast<float *>(s_slot + kPcSegs);
+      int32_t *s_idx = reinterpret_cast<int32_t *>(s_scale + kPcSegs);
+      float *s_wout = reinterpret_cast<float *>(s_idx + kPcRows), *s_win = s_wout + kPcRows;
+      const int64_t s0 = (int64_t)t * T;
+      const int nseg = (int)min((int64_t)T, S - s0);
+      const int32_t p0 = __ldg(a.key + s0), p1 = __ldg(a.key + s0 + nseg);
+      for (int i = lane; i <= nseg; i += 32) s_key[i] = __ldg(a.key + s0 + i);
+      for (int i = lane; i < nseg; i += 32) {
+        s_slot[i] = __ldg(a.seg_slot + s0 + i);
+        s_scale[i] = edge_scale(a, __ldg(a.seg_edge + s0 + i));
+      }
+      const int nidx = min(p1 - p0, kPcRows);
+      for (int i = lane; i < nidx; i += 32) {
+        const uint32_t c = (uint32_t)__ldg(fa.cflag + p0 + i);
+        s_idx[i] = (int32_t)c;
+        s_wout[i] = a.a_out ? __ldg(a.a_out + (c & kIdMask)) : 1.0f;
+        s_win[i] = a.a_in ? __ldg(a.a_in + (c & kIdMask)) : 1.0f;
+      }
+      __syncwarp();
+      for (int32_t pb = p0; pb < p1; pb += 32) {        // zero-fill first-touched rows (flags 32 at a time)
+        const int32_t p = pb + lane;
+        uint32_t c = 0;
+        if (p < p1) c = (uint32_t)(p - p0 < kPcRows ? s_idx[p - p0] : __ldg(fa.cflag + p));
+        unsigned m = __ballot_sync(kFull, (c & kFirst) && !(c & kExcl));
+        while (m) {
+          int bsel = -1;
+#pragma unroll
+          for (int g = 0; g < G::kSub; ++g) {
+            if (m) {
+              const int bit = __ffs(m) - 1;
+              m &= m - 1;
+              if (g == sub) bsel = bit;
+            }
+          }
+          const uint32_t cv = __shfl_sync(kFull, c, bsel < 0 ? 0 : bsel);
+          if (bsel >= 0) {
+            float *yp = a.Y + (int64_t)(cv & kIdMask) * F + col;
+#pragma unroll
+            for (int j = 0; j < VPL; ++j)
+              if (col_ok<SW, VPL, EXACT>(col, j, F)) st_zero_v4(yp + j * G::kColStride);
+          }
+        }
+      }
+      const int64_t i0 = fa.niso * t / fa.ntiles, i1 = fa.niso * (t + 1) / fa.ntiles;
+      for (int64_t ib = i0; ib < i1; ib += 32) {        // this tile's share of the isolated vertices
+        const int n = (int)min((int64_t)32, i1 - ib);
+        const int32_t my_v = lane < n ? __ldg(fa.iso + ib + lane) : 0;
+        for (int r0 = 0; r0 < n; r0 += G::kSub) {
+          const int r = r0 + sub;
+          const int32_t v = __shfl_sync(kFull, my_v, r & 31);
+          if (r < n) {
+            float *yp = a.Y + (int64_t)v * F + col;
+#pragma unroll
+            for (int j = 0; j < VPL; ++j)
+              if (col_ok<SW, VPL, EXACT>(col, j, F)) st_zero_v4(yp + j * G::kColStride);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        st_relaxed(done + t, 1);
+        red_relaxed_inc(blk_cnt + (t >> 5));
+        s_tile[b] = t;
+        s_cursor[b] = 0;
+      }
+      wait_zero_fill(fa.ctrl, fa.nblk, t, lane, blk_wm);   // every earlier tile is published too
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_full[b]);
+    }
+    return;
+  }
+
+  // ------------------------------ consumers ------------------------------
+  float *ring = reinterpret_cast<float *>(smem + NB * kPcBufInts) + (warp - NP) * (2 * G::kUnroll * VPL * 32 * 4);
+  bool finished[NP];
+#pragma unroll
+  for (int p = 0; p < NP; ++p) finished[p] = false;
+  int nfinished = 0;
+  for (int it = 0; nfinished < NP; ++it) {
+    const int p = it % NP;
+    bool skip = false;
+#pragma unroll
+    for (int q = 0; q < NP; ++q) if (q == p && finished[q]) skip = true;
+    if (skip) continue;
+    const int b = it % NB;
+    mbar_wait(&s_full[b], (it / NB) & 1);
+    const int t = s_tile[b];
+    if (t < 0) {
+#pragma unroll
+      for (int q = 0; q < NP; ++q) if (q == p) finished[q] = true;
+      ++nfinished;
+      continue;
+    }
+    const int32_t *s_key = buf_key(b), *s_slot = s_key + (kPcSegs + 1 + 3) / 4 * 4;
+    const float *s_scale = reinterpret_cast<const float *>(s_slot + kPcSegs);
+    const int32_t *s_idx = reinterpret_cast<const int32_t *>(s_scale + kPcSegs);
+    const float *s_wout = reinterpret_cast<const float *>(s_idx + kPcRows), *s_win = s_wout + kPcRows;
+    const int nseg = (int)min((int64_t)T, S - (int64_t)t * T);
+    const int32_t p0 = s_key[0];
+    auto row_idx = [&](int32_t q) -> uint32_t {
+      return (uint32_t)(q - p0 < kPcRows ? s_idx[q - p0] : __ldg(fa.cflag + q));
+    };
+    auto row_win = [&](int32_t q, uint32_t v) -> float {
+      return q - p0 < kPcRows ? s_win[q - p0] : (a.a_in ? __ldg(a.a_in + v) : 1.0f);
+    };
+    auto row_wout = [&](int32_t q, uint32_t v) -> float {
+      return q - p0 < kPcRows ? s_wout[q - p0] : (a.a_out ? __ldg(a.a_out + v) : 1.0f);
+    };
+    auto ring_slot = [&](int buf, int u, int j) {
+      return ring + ((((buf * G::kUnroll) + u) * VPL + j) * 32 + lane) * 4;
+    };
+    for (;;) {
+      int j0 = 0;
+      if (lane == 0) j0 = atomicAdd(&s_cursor[b], kPcRun * G::kSub);
+      j0 = __shfl_sync(kFull, j0, 0);
+      if (j0 >= nseg) break;
+      // this sub-warp's run of segments [i_lo, i_hi) and its rows [plo, phi)
+      const int i_lo = min(j0 + sub * kPcRun, nseg), i_hi = min(i_lo + kPcRun, nseg);
+      const int32_t plo = s_key[i_lo], phi = s_key[i_hi];
+      auto issue = [&](int buf, int32_t q) {
+#pragma unroll
+        for (int u = 0; u < G::kUnroll; ++u) {
+          if (q + u < phi) {
+            const float *xp = a.X + (int64_t)(row_idx(q + u) & kIdMask) * F + col;
+#pragma unroll
+            for (int j = 0; j < VPL; ++j)
+              if (col_ok<SW, VPL, EXACT>(col, j, F)) cp_async16(ring_slot(buf, u, j), xp + j * G::kColStride);
+          }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      };
+      int i = i_lo;
+      while (i < i_hi && s_key[i + 1] == s_key[i]) ++i;
+      int32_t seg_end = i < i_hi ? s_key[i + 1] : phi;
+      Acc<VPL> acc;
+      acc.zero();
+      int buf = 0;
+      issue(0, plo);
+      for (int32_t q = plo; q < phi; q += G::kUnroll) {
+        issue(buf ^ 1, q + G::kUnroll);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+#pragma unroll
+        for (int u = 0; u < G::kUnroll; ++u) {
+          if (q + u < phi) {
+            const float w = a.a_in ? row_win(q + u, row_idx(q + u) & kIdMask) : 1.0f;
+#pragma unroll
+            for (int j = 0; j < VPL; ++j) {
+              if (col_ok<SW, VPL, EXACT>(col, j, F)) {
+                const float4 x = *reinterpret_cast<const float4 *>(ring_slot(buf, u, j));
+                acc.v[j].x = fmaf(w, x.x, acc.v[j].x);
+                acc.v[j].y = fmaf(w, x.y, acc.v[j].y);
+                acc.v[j].z = fmaf(w, x.z, acc.v[j].z);
+                acc.v[j].w = fmaf(w, x.w, acc.v[j].w);
+              }
+            }
+            if (q + u + 1 == seg_end) {
+              const int32_t slot = s_slot[i];
+              if (slot >= 0) {
+                float *sp = a.scratch + (int64_t)slot * F + col;
+#pragma unroll
+                for (int j = 0; j < VPL; ++j)
+                  if (col_ok<SW, VPL, EXACT>(col, j, F)) red_add_v4(sp + j * G::kColStride, acc.v[j]);
+              } else {
+                scale_acc<VPL>(acc, s_scale[i]);
+#pragma unroll 2
+                for (int32_t r = s_key[i]; r < seg_end; ++r) {
+                  const uint32_t c = row_idx(r);
+                  const float o = row_wout(r, c & kIdMask);
+                  float *yp = a.Y + (int64_t)(c & kIdMask) * F + col;
+                  if (c & kExcl) {
+#pragma unroll
+                    for (int j = 0; j < VPL; ++j)
+                      if (col_ok<SW, VPL, EXACT>(col, j, F))
+                        st_v4(yp + j * G::kColStride, make_float4(acc.v[j].x * o, acc.v[j].y * o, acc.v[j].z * o,
+                                                                  acc.v[j].w * o));
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < VPL; ++j)
+                      if (col_ok<SW, VPL, EXACT>(col, j, F))
+                        red_add_v4(yp + j * G::kColStride, make_float4(acc.v[j].x * o, acc.v[j].y * o,
+                                                                       acc.v[j].z * o, acc.v[j].w * o));
+                  }
+                }
+              }
+              acc.zero();
+              ++i;
+              while (i < i_hi && s_key[i + 1] == s_key[i]) ++i;
+              seg_end = i < i_hi ? s_key[i + 1] : phi;
+            }
+          }
+        }
+        buf ^= 1;
+      }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s_empty[b]);
+  }
+}
+
 // Pass 2 for heavy hyperedges with the single-writer flags (rows that were never zero-filled
 // must be stored, not reduced).
 template <int SW, int VPL>
@@ -430,7 +700,7 @@ int launch(hgPlan *plan, FusedArgs &fa, cudaStream_t s) {
   const size_t smem = (size_t)kWarpsPerBlock * 2 * kBufInts * sizeof(int32_t) +
                       (size_t)kWarpsPerBlock * 2 * G::kUnroll * VPL * 32 * sizeof(float4);
   HG_CUDA_TRY(cudaFuncSetAttribute(fused_kernel<SW, VPL, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   227 * 1024));
+                                   (int)smem));
   int per_sm = 0;
   HG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_kernel<SW, VPL, EXACT>, kThreads, smem));
   if (per_sm < 1) per_sm = 1;
@@ -446,6 +716,48 @@ int launch(hgPlan *plan, FusedArgs &fa, cudaStream_t s) {
   fa.ctrl = plan->ctrl;
   fa.a.nwork = plan->nseg;
   fused_kernel<SW, VPL, EXACT><<<(unsigned)grid, kThreads, smem, s>>>(fa);
+  HG_CUDA_TRY(cudaGetLastError());
+  if (plan->nheavy_segs > 0) {
+    fa.a.nwork = plan->nheavy_segs;
+    fa.a.seg_list = plan->heavy_segs;
+    int64_t g2 = ceil_div<int64_t>(plan->nheavy_segs, kWarpsPerBlock * G::kSub);
+    if (g2 > (int64_t)plan->sm_count * 8) g2 = (int64_t)plan->sm_count * 8;
+    fused_pass2_kernel<SW, VPL><<<(unsigned)g2, kThreads, 0, s>>>(fa);
+    HG_CUDA_TRY(cudaGetLastError());
+  }
+  return HG_OK;
+}
+
+template <int SW, int VPL, bool EXACT, int NW, int NP, int NB>
+int launch_pc(hgPlan *plan, FusedArgs &fa, cudaStream_t s) {
+  using G = Geo<SW, VPL>;
+  const int F = fa.a.F;
+  const double avg_len = (double)plan->nnz / (double)plan->nseg;
+  static const double tile_env = getenv("HGEF_PC_TILE_KB") ? atof(getenv("HGEF_PC_TILE_KB")) : 0.0;
+  const double tile_kb = tile_env > 0 ? tile_env : 256.0;
+  int T = (int)(tile_kb * 1024.0 / (avg_len * 4.0 * F * 2.0));
+  const int cap_T = (int)(0.8 * kPcRows / avg_len);
+  if (T > cap_T) T = cap_T;
+  if (T > kPcSegs) T = kPcSegs;
+  if (T < 8) T = 8;
+  fa.tile_segs = T;
+  fa.ntiles = (int32_t)ceil_div<int64_t>(plan->nseg, T);
+  fa.nblk = (fa.ntiles + 31) / 32;
+  const size_t smem = (size_t)NB * kPcBufInts * sizeof(int32_t) +
+                      (size_t)(NW - NP) * 2 * G::kUnroll * VPL * 32 * sizeof(float4);
+  auto kern = pc_kernel<SW, VPL, EXACT, NW, NP, NB>;
+  HG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  HG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NW * 32, smem));
+  HG_REQUIRE(per_sm >= 1, "launch_pc: kernel does not fit an SM (smem %zu)", smem);
+  static const int ctas_env = getenv("HGEF_CTAS_PER_SM") ? atoi(getenv("HGEF_CTAS_PER_SM")) : 0;
+  if (ctas_env > 0 && ctas_env < per_sm) per_sm = ctas_env;
+  int64_t grid = (int64_t)plan->sm_count * per_sm;
+  if (grid > fa.ntiles) grid = fa.ntiles;
+  HG_CUDA_TRY(cudaMemsetAsync(plan->ctrl, 0, (size_t)(fa.ntiles + fa.nblk + 8) * sizeof(int32_t), s));
+  fa.ctrl = plan->ctrl;
+  fa.a.nwork = plan->nseg;
+  kern<<<(unsigned)grid, NW * 32, smem, s>>>(fa);
   HG_CUDA_TRY(cudaGetLastError());
   if (plan->nheavy_segs > 0) {
     fa.a.nwork = plan->nheavy_segs;
@@ -500,6 +812,15 @@ int launch_fused(hgPlan *plan, const dev::Args &base, cudaStream_t s) {
   while (sw < 32 && F > sw * 16) sw *= 2;  // at most 4 vectors per lane
   const int vpl = F <= sw * 4 ? 1 : (F <= sw * 8 ? 2 : 4);
   const bool exact = F == sw * 4 * vpl;
+  static const int pc = getenv("HGEF_PC") ? atoi(getenv("HGEF_PC")) : 0;   // A/B: 1 = 16 warps / 2 producers, 2 = 16 / 4
+  if (pc && exact) {
+#define HG_PC_CASE(SW_, VPL_)                                                                  \
+    if (sw == SW_ && vpl == VPL_)                                                              \
+      return pc == 2 ? launch_pc<SW_, VPL_, true, 16, 4, 8>(plan, fa, s)                        \
+                     : launch_pc<SW_, VPL_, true, 16, 2, 4>(plan, fa, s)
+    HG_PC_CASE(8, 1); HG_PC_CASE(8, 2); HG_PC_CASE(16, 2); HG_PC_CASE(32, 1); HG_PC_CASE(32, 2); HG_PC_CASE(32, 4);
+#undef HG_PC_CASE
+  }
 #define HG_CASE(SW_, VPL_)                                               \
   if (sw == SW_ && vpl == VPL_)                                          \
     return exact ? launch<SW_, VPL_, true>(plan, fa, s) : launch<SW_, VPL_, false>(plan, fa, s)

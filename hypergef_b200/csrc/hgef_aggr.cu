@@ -24,6 +24,8 @@ namespace hg {
 bool fused_available(const hgPlan *plan, int F, bool force);
 int launch_fused(hgPlan *plan, const dev::Args &base, cudaStream_t s);
 int fused_check(hgPlan *plan, cudaStream_t s);
+bool pull_available(const hgPlan *plan, int F, bool force);
+int launch_pull_any(hgPlan *plan, const dev::Args &base, cudaStream_t s);
 namespace {
 using namespace dev;
 
@@ -223,6 +225,14 @@ int hg_aggr_forward(hgPlan *plan, const float *d_X, const float *d_s1, const flo
   cudaStream_t s = (cudaStream_t)stream;
   const bool vec = F % 4 == 0 && F <= 512 && !(flags & HG_FORCE_SCALAR) && aligned16(d_X) && aligned16(d_Y);
   // single-launch persistent form: zero-fill happens inside the kernel (hgef_fused.cu)
+  // gather-only two-phase form (no reductions): the fastest when it applies (hgef_fused.cu)
+  const bool pull = vec && !(flags & (HG_ACCUMULATE | HG_TWO_PASS | HG_FORCE_FUSED)) &&
+                    pull_available(plan, F, (flags & HG_FORCE_PULL) != 0);
+  if (pull) {
+    Args pa{};
+    pa.X = d_X; pa.s1 = d_s1; pa.s2 = d_s2; pa.a_out = d_a_out; pa.a_in = d_a_in; pa.Y = d_Y; pa.F = F;
+    return launch_pull_any(plan, pa, s);
+  }
   const bool fused = vec && !(flags & (HG_ACCUMULATE | HG_TWO_PASS)) && fused_available(plan, F, (flags & HG_FORCE_FUSED) != 0);
   if (!fused && !(flags & HG_ACCUMULATE))
     HG_CUDA_TRY(cudaMemsetAsync(d_Y, 0, (size_t)plan->num_nodes * F * sizeof(float), s));

@@ -637,6 +637,224 @@ __global__ void __launch_bounds__(NW * 32) pc_kernel(const FusedArgs fa) {
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// PULL form: no reductions at all.  Replaying the address stream of the workload with a trivially
+// lean kernel (tools/replay.cu, profiles/r01_replay_address_stream.txt) shows where the time of every
+// scatter-based variant goes: gathering the 2.2 M member rows takes 85 us, issuing the same number
+// of red.v4 takes 310-410 us.  Loads are several times cheaper than L2 reductions on this part, so
+// the aggregation is done as two gather passes over the same streaming machinery:
+//   phase A  (units = balancer segments)   Xe[e] = s1[e] s2[e] * sum_{u in seg} a_in[u] X[u]
+//            light hyperedge: one plain 128-bit store per 16 B; heavy (w > 1): red into the
+//            pre-zeroed Xe row (rare)
+//   phase B  (units = vertices, CSR of H)  Y[v]  = a_out[v] * sum_{e in H[v]} Xe[e]
+//            plain stores, every Y row written exactly once, no zero-fill, no ordering protocol,
+//            and a fixed summation order per row (bit-reproducible run to run).
+// Xe ([M, F]) goes through L2 / HBM between the phases: M < N rows, and a replica's worth of it is
+// L2-resident when phase B reads it.  DRAM bytes ~ 8FN + 8FM instead of 8FN, but at gather speed.
+struct PullArgs {
+  const int32_t *ptr;       // unit offsets: A = balancer key [S+1], B = H indptr [N+1]
+  const int32_t *ind;       // gathered row of every position: A = H^T colind (vertex), B = H colind (hyperedge)
+  const int32_t *out_row;   // A: seg_edge [S]; B: NULL (the unit is the row)
+  const int32_t *slot;      // A: seg_slot [S] (>= 0: heavy, reduce into the pre-zeroed row); B: NULL
+  const float *src;         // A: X; B: Xe
+  const float *w_in;        // A: a_in (or NULL); B: NULL
+  const float *w_out1, *w_out2;   // A: s1, s2 per hyperedge; B: a_out per vertex, NULL
+  float *dst;               // A: Xe; B: Y
+  int32_t *counter;
+  int64_t nunit;
+  int32_t F, tile;
+};
+
+constexpr int kPullUnits = 96;   // units (segments / vertices) per warp tile
+constexpr int kPullHdr = (kPullUnits + 1 + 2 * kPullUnits + 3) / 4 * 4;   // key[T+1] orow[T] oscale[T]
+constexpr int kPullBuf = kPullHdr + 2 * kIdxCap;                          // + idx[] win[]
+
+template <int SW, int VPL>
+struct PullGeo {   // ring depth: 8 (rows >= 512 B) or 4 sixteen-byte vectors per lane and step
+  static constexpr int kUnroll = (SW * VPL >= 32 ? 8 : 4) / VPL;
+};
+
+template <int SW, int VPL, bool EXACT>
+__global__ void __launch_bounds__(kThreads) pull_kernel(const PullArgs pa) {
+  using G = Geo<SW, VPL>;
+  constexpr int U = PullGeo<SW, VPL>::kUnroll;
+  extern __shared__ __align__(16) int32_t smem[];
+  const int T = pa.tile;                                    // <= kPullUnits
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int32_t *wbuf = smem + warp * 2 * kPullBuf;
+  float *ring = reinterpret_cast<float *>(smem + kWarpsPerBlock * 2 * kPullBuf) + warp * (2 * U * VPL * 32 * 4);
+  const int sub = lane / SW;
+  const int col = (lane % SW) * 4;
+  const int F = EXACT ? SW * 4 * VPL : pa.F;
+  const int64_t ntile = (pa.nunit + T - 1) / T;
+
+  auto claim = [&]() {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(pa.counter, 1);
+    return __shfl_sync(kFull, t, 0);
+  };
+  // stage tile t into buffer b: unit bounds, output row / scale per unit, gathered-row indices and weights
+  auto stage = [&](int t, int b) {
+    int32_t *s_key = wbuf + b * kPullBuf, *s_orow = s_key + kPullUnits + 1;
+    float *s_oscale = reinterpret_cast<float *>(s_orow + kPullUnits);
+    int32_t *s_idx = s_key + kPullHdr;
+    float *s_win = reinterpret_cast<float *>(s_idx + kIdxCap);
+    const int64_t u0 = (int64_t)t * T;
+    const int nu = (int)min((int64_t)T, pa.nunit - u0);
+    const int32_t p0 = __ldg(pa.ptr + u0), p1 = __ldg(pa.ptr + u0 + nu);
+    for (int i = lane; i < nu; i += 32) {
+      const int32_t k = __ldg(pa.ptr + u0 + i), k_next = __ldg(pa.ptr + u0 + i + 1);
+      const int32_t orow = pa.out_row ? __ldg(pa.out_row + u0 + i) : (int32_t)(u0 + i);
+      float sc = pa.w_out1 ? __ldg(pa.w_out1 + orow) : 1.0f;
+      if (pa.w_out2) sc *= __ldg(pa.w_out2 + orow);
+      const bool heavy = pa.slot && __ldg(pa.slot + u0 + i) >= 0;
+      s_key[i] = k;
+      s_orow[i] = heavy ? ~orow : orow;                     // (negative = heavy: reduce, do not store)
+      s_oscale[i] = sc;
+      // a unit with no member produces a zero row (phase B: vertices in no hyperedge)
+      if (k_next == k && !pa.out_row)
+        for (int c0 = 0; c0 < F; c0 += 4) st_zero_v4(pa.dst + (int64_t)orow * F + c0);
+    }
+    if (lane == 0) s_key[nu] = p1;
+    const int nidx = min(p1 - p0, kIdxCap);
+    for (int i = lane; i < nidx; i += 32) {
+      const int32_t v = __ldg(pa.ind + p0 + i);
+      s_idx[i] = v;
+      s_win[i] = pa.w_in ? __ldg(pa.w_in + v) : 1.0f;
+    }
+    __syncwarp();
+  };
+
+  int t = claim(), cb = 0;
+  if (t >= ntile) return;
+  stage(t, 0);
+  for (;;) {
+    const int t_next = claim();
+    if (t_next < ntile) stage(t_next, cb ^ 1);
+    const int32_t *s_key = wbuf + cb * kPullBuf, *s_orow = s_key + kPullUnits + 1;
+    const float *s_oscale = reinterpret_cast<const float *>(s_orow + kPullUnits);
+    const int32_t *s_idx = s_key + kPullHdr;
+    const float *s_win = reinterpret_cast<const float *>(s_idx + kIdxCap);
+    const int nu = (int)min((int64_t)T, pa.nunit - (int64_t)t * T);
+    const int32_t p0 = s_key[0];
+    auto row_idx = [&](int32_t q) -> int32_t { return q - p0 < kIdxCap ? s_idx[q - p0] : __ldg(pa.ind + q); };
+    auto row_win = [&](int32_t q, int32_t v) -> float {
+      return q - p0 < kIdxCap ? s_win[q - p0] : (pa.w_in ? __ldg(pa.w_in + v) : 1.0f);
+    };
+    // contiguous runs of units per sub-warp, balanced by row count (first unit whose start >= target)
+    auto first_unit_at = [&](int32_t target) {
+      int lo = 0, hi = nu;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (s_key[mid] < target) lo = mid + 1; else hi = mid;
+      }
+      return lo;
+    };
+    const int32_t rows = s_key[nu] - p0;
+    const int i_lo = G::kSub > 1 && sub > 0 ? first_unit_at(p0 + (int32_t)(((int64_t)rows * sub) / G::kSub)) : 0;
+    const int i_hi = G::kSub > 1 && sub + 1 < G::kSub
+                         ? first_unit_at(p0 + (int32_t)(((int64_t)rows * (sub + 1)) / G::kSub)) : nu;
+    const int32_t plo = s_key[i_lo], phi = s_key[i_hi];
+    auto ring_slot = [&](int buf, int u, int j) { return ring + ((((buf * U) + u) * VPL + j) * 32 + lane) * 4; };
+    auto issue = [&](int buf, int32_t q) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (q + u < phi) {
+          const float *xp = pa.src + (int64_t)row_idx(q + u) * F + col;
+#pragma unroll
+          for (int j = 0; j < VPL; ++j)
+            if (col_ok<SW, VPL, EXACT>(col, j, F)) cp_async16(ring_slot(buf, u, j), xp + j * G::kColStride);
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int i = i_lo;
+    while (i < i_hi && s_key[i + 1] == s_key[i]) ++i;
+    int32_t unit_end = i < i_hi ? s_key[i + 1] : phi;
+    Acc<VPL> acc;
+    acc.zero();
+    int buf = 0;
+    issue(0, plo);
+    for (int32_t q = plo; q < phi; q += U) {
+      issue(buf ^ 1, q + U);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (q + u < phi) {
+          const float w = pa.w_in ? row_win(q + u, row_idx(q + u)) : 1.0f;
+#pragma unroll
+          for (int j = 0; j < VPL; ++j) {
+            if (col_ok<SW, VPL, EXACT>(col, j, F)) {
+              const float4 x = *reinterpret_cast<const float4 *>(ring_slot(buf, u, j));
+              acc.v[j].x = fmaf(w, x.x, acc.v[j].x);
+              acc.v[j].y = fmaf(w, x.y, acc.v[j].y);
+              acc.v[j].z = fmaf(w, x.z, acc.v[j].z);
+              acc.v[j].w = fmaf(w, x.w, acc.v[j].w);
+            }
+          }
+          if (q + u + 1 == unit_end) {       // unit i complete: one output row
+            const int32_t orow = s_orow[i];
+            scale_acc<VPL>(acc, s_oscale[i]);
+            float *op = pa.dst + (int64_t)(orow < 0 ? ~orow : orow) * F + col;
+#pragma unroll
+            for (int j = 0; j < VPL; ++j) {
+              if (col_ok<SW, VPL, EXACT>(col, j, F)) {
+                if (orow < 0) red_add_v4(op + j * G::kColStride, acc.v[j]);
+                else st_v4(op + j * G::kColStride, acc.v[j]);
+              }
+            }
+            acc.zero();
+            ++i;
+            while (i < i_hi && s_key[i + 1] == s_key[i]) ++i;
+            unit_end = i < i_hi ? s_key[i + 1] : phi;
+          }
+        }
+      }
+      buf ^= 1;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    if (t_next >= ntile) break;
+    t = t_next;
+    cb ^= 1;
+  }
+}
+
+// zero the Xe rows of heavy hyperedges (their segments reduce into them in phase A)
+__global__ void pull_zero_heavy_kernel(int64_t nheavy_segs, const int32_t *__restrict__ heavy_segs,
+                                       const int32_t *__restrict__ seg_edge, float *__restrict__ xe, int F) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (w >= nheavy_segs) return;
+  float *row = xe + (int64_t)seg_edge[heavy_segs[w]] * F;
+  for (int c = lane; c < F; c += 32) row[c] = 0.0f;
+}
+
+template <int SW, int VPL, bool EXACT>
+int launch_pull_phase(const hgPlan *plan, PullArgs &pa, cudaStream_t s) {
+  using G = Geo<SW, VPL>;
+  const double avg_len = (double)plan->nnz / (double)pa.nunit;
+  int T = (int)(0.75 * kIdxCap / (avg_len > 1.0 ? avg_len : 1.0));
+  if (T > kPullUnits) T = kPullUnits;
+  if (T < G::kSub) T = G::kSub;
+  pa.tile = T;
+  const size_t smem = (size_t)kWarpsPerBlock * 2 * kPullBuf * sizeof(int32_t) +
+                      (size_t)kWarpsPerBlock * 2 * PullGeo<SW, VPL>::kUnroll * VPL * 32 * sizeof(float4);
+  auto kern = pull_kernel<SW, VPL, EXACT>;
+  HG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  HG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+  if (per_sm < 1) per_sm = 1;
+  static const int ctas_env = getenv("HGEF_PULL_CTAS") ? atoi(getenv("HGEF_PULL_CTAS")) : 0;
+  if (ctas_env > 0 && ctas_env < per_sm) per_sm = ctas_env;
+  int64_t grid = (int64_t)plan->sm_count * per_sm;
+  const int64_t max_useful = ceil_div<int64_t>(ceil_div<int64_t>(pa.nunit, T), kWarpsPerBlock);
+  if (grid > max_useful) grid = max_useful;
+  kern<<<(unsigned)grid, kThreads, smem, s>>>(pa);
+  HG_CUDA_TRY(cudaGetLastError());
+  return HG_OK;
+}
+
 // Pass 2 for heavy hyperedges with the single-writer flags (rows that were never zero-filled
 // must be stored, not reduced).
 template <int SW, int VPL>
@@ -770,6 +988,29 @@ int launch_pc(hgPlan *plan, FusedArgs &fa, cudaStream_t s) {
   return HG_OK;
 }
 
+template <int SW, int VPL, bool EXACT>
+int launch_pull(hgPlan *plan, const dev::Args &a, cudaStream_t s) {
+  const int F = a.F;
+  HG_CUDA_TRY(cudaMemsetAsync(plan->ctrl, 0, 8 * sizeof(int32_t), s));
+  if (plan->nheavy_segs > 0) {
+    pull_zero_heavy_kernel<<<(unsigned)ceil_div<int64_t>(plan->nheavy_segs * 32, 256), 256, 0, s>>>(
+        plan->nheavy_segs, plan->heavy_segs, plan->seg_edge, plan->xe, F);
+    HG_CUDA_TRY(cudaGetLastError());
+  }
+  PullArgs A{};
+  A.ptr = plan->key; A.ind = plan->colind; A.out_row = plan->seg_edge; A.slot = plan->seg_slot;
+  A.src = a.X; A.w_in = a.a_in; A.w_out1 = a.s1; A.w_out2 = a.s2; A.dst = plan->xe;
+  A.counter = plan->ctrl; A.nunit = plan->nseg; A.F = F;
+  static const int only = getenv("HGEF_PULL_ONLY") ? atoi(getenv("HGEF_PULL_ONLY")) : 0;  // timing: 1 = A, 2 = B
+  if (only != 2)
+    if (int rc = launch_pull_phase<SW, VPL, EXACT>(plan, A, s)) return rc;
+  if (only == 1) return HG_OK;
+  PullArgs B{};
+  B.ptr = plan->h_ptr; B.ind = plan->h_ind; B.src = plan->xe; B.w_out1 = a.a_out; B.dst = a.Y;
+  B.counter = plan->ctrl + 4; B.nunit = plan->num_nodes; B.F = F;
+  return launch_pull_phase<SW, VPL, EXACT>(plan, B, s);
+}
+
 }  // namespace
 
 int fused_check(hgPlan *plan, cudaStream_t s) {
@@ -794,6 +1035,54 @@ bool fused_available(const hgPlan *plan, int F, bool force) {
   if (force) return true;
   if ((double)plan->num_nodes * F * 4.0 < 64.0 * 1048576.0) return false;
   return (double)plan->nnz / (double)plan->nseg <= 0.125 * kIdxCap;
+}
+
+// The pull form needs H (built by the plan), short units on both sides (staging) and no extreme
+// vertex degree (one sub-warp walks a vertex's hyperedges).
+bool pull_available(const hgPlan *plan, int F, bool force) {
+  if (plan->h_ptr == nullptr || plan->ctrl == nullptr) return false;
+  if (plan->max_vdeg > 4096) return false;
+  if (force) return true;
+  if ((double)plan->num_nodes * F * 4.0 < 64.0 * 1048576.0) return false;
+  // measured crossover (profiles/r01_tuning_sweeps.txt): the gather-only form wins for rows up to 512 B
+  // (F=32/64/128: 160/216/400 us vs 184/274/454 us), the scatter form from F=256 up (747 vs 754 us, 1410 vs 1683)
+  if (F > 128) return false;
+  return (double)plan->nnz / (double)plan->nseg <= 0.125 * kIdxCap;
+}
+
+int ensure_xe(hgPlan *plan, int F, cudaStream_t s) {
+  const size_t need = (size_t)plan->num_edges * F;
+  if (need <= plan->xe_floats) return HG_OK;
+  HG_CUDA_TRY(cudaStreamSynchronize(s));
+  cudaFree(plan->xe);
+  plan->xe = nullptr;
+  plan->xe_floats = 0;
+  if (cudaMalloc((void **)&plan->xe, need * sizeof(float)) != cudaSuccess) {
+    cudaGetLastError();
+    return set_error(HG_ENOMEM, "aggr_forward: cannot allocate %zu bytes for the hyperedge features", need * sizeof(float));
+  }
+  plan->xe_floats = need;
+  return HG_OK;
+}
+
+int launch_pull_any(hgPlan *plan, const dev::Args &base, cudaStream_t s) {
+  if (int rc = ensure_xe(plan, base.F, s)) return rc;
+  const int F = base.F;
+  int sw = F <= 16 ? 4 : (F <= 64 ? 8 : (F <= 128 ? 16 : 32));
+  static const int sw_env = getenv("HGEF_PULL_SW") ? atoi(getenv("HGEF_PULL_SW")) : 0;
+  if (sw_env == 4 || sw_env == 8 || sw_env == 16 || sw_env == 32) sw = sw_env;
+  while (sw < 32 && F > sw * 16) sw *= 2;
+  const int vpl = F <= sw * 4 ? 1 : (F <= sw * 8 ? 2 : 4);
+  const bool exact = F == sw * 4 * vpl;
+#define HG_CASE(SW_, VPL_)                                               \
+  if (sw == SW_ && vpl == VPL_)                                          \
+    return exact ? launch_pull<SW_, VPL_, true>(plan, base, s) : launch_pull<SW_, VPL_, false>(plan, base, s)
+  HG_CASE(4, 1); HG_CASE(4, 2); HG_CASE(4, 4);
+  HG_CASE(8, 1); HG_CASE(8, 2); HG_CASE(8, 4);
+  HG_CASE(16, 1); HG_CASE(16, 2); HG_CASE(16, 4);
+  HG_CASE(32, 1); HG_CASE(32, 2); HG_CASE(32, 4);
+#undef HG_CASE
+  return set_error(HG_EINVAL, "launch_pull: no kernel for F=%d", F);
 }
 
 // Y is NOT zero-filled by the caller; scratch (if any) is.

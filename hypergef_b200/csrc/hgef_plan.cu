@@ -156,6 +156,25 @@ __global__ void iso_list_kernel(int64_t n, const int32_t *__restrict__ iso,
   if (v < n && iso[v]) list[pos[v] - 1] = (int32_t)v;
 }
 
+// (vertex, hyperedge) pair of every index position, for the transposition H^T -> H
+__global__ void pos_pairs_kernel(int64_t nseg, const int32_t *__restrict__ key, const int32_t *__restrict__ seg_edge,
+                                 const int32_t *__restrict__ colind, int64_t *__restrict__ rows,
+                                 int64_t *__restrict__ cols) {
+  const int lane = threadIdx.x & 31;
+  int64_t s = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;   // one warp per segment
+  if (s >= nseg) return;
+  const int32_t e = seg_edge[s];
+  for (int32_t p = key[s] + lane; p < key[s + 1]; p += 32) {
+    rows[p] = colind[p];
+    cols[p] = e;
+  }
+}
+
+__global__ void max_deg_kernel(int64_t n, const int32_t *__restrict__ ptr, int *__restrict__ out) {
+  int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (v < n) atomicMax(out, ptr[v + 1] - ptr[v]);
+}
+
 #define GRID(n) (unsigned)ceil_div<int64_t>((n), 256), 256
 
 template <typename In, typename Out, typename Op, typename T>
@@ -210,6 +229,38 @@ int build_fused(hgPlan *p, cudaStream_t s) {
     iso_list_kernel<<<GRID(N), 0, s>>>(N, iso.p, pos.p, p->iso_list);
     HG_CUDA_TRY(cudaGetLastError());
   }
+  HG_CUDA_TRY(cudaStreamSynchronize(s));
+  return HG_OK;
+}
+
+// H (vertex -> hyperedges, ascending) by transposing the caller's H^T with the CSR builder
+int build_pull(hgPlan *p, cudaStream_t s) {
+  const int64_t N = p->num_nodes, M = p->num_edges, Z = p->nnz;
+  if (Z == 0 || N == 0 || M == 0) return HG_OK;
+  DevBuf<int64_t> rows, cols;
+  DevBuf<int32_t> t_ptr, t_ind;
+  DevBuf<float> data, t_data;
+  DevBuf<int> mx;
+  HG_CUDA_TRY(rows.alloc(Z)); HG_CUDA_TRY(cols.alloc(Z));
+  HG_CUDA_TRY(t_ptr.alloc(M + 1)); HG_CUDA_TRY(t_ind.alloc(Z));
+  HG_CUDA_TRY(data.alloc(Z)); HG_CUDA_TRY(t_data.alloc(Z)); HG_CUDA_TRY(mx.alloc(1));
+  HG_CUDA_TRY(cudaMalloc((void **)&p->h_ptr, (size_t)(N + 1) * sizeof(int32_t)));
+  HG_CUDA_TRY(cudaMalloc((void **)&p->h_ind, (size_t)Z * sizeof(int32_t)));
+  pos_pairs_kernel<<<(unsigned)ceil_div<int64_t>(p->nseg * 32, 256), 256, 0, s>>>(p->nseg, p->key, p->seg_edge,
+                                                                                  p->colind, rows.p, cols.p);
+  HG_CUDA_TRY(cudaGetLastError());
+  int64_t z = 0;
+  if (int rc = hg_csr_build_dev(N, M, Z, rows.p, cols.p, p->h_ptr, p->h_ind, data.p, t_ptr.p, t_ind.p, t_data.p,
+                                &z, p->device, (void *)s))
+    return rc;
+  if (z != Z) {  // a vertex listed twice in one hyperedge: the pull form would count it once
+    cudaFree(p->h_ptr); cudaFree(p->h_ind);
+    p->h_ptr = p->h_ind = nullptr;
+    return HG_OK;
+  }
+  HG_CUDA_TRY(cudaMemsetAsync(mx.p, 0, sizeof(int), s));
+  max_deg_kernel<<<GRID(N), 0, s>>>(N, p->h_ptr, mx.p);
+  HG_CUDA_TRY(cudaMemcpyAsync(&p->max_vdeg, mx.p, sizeof(int), cudaMemcpyDeviceToHost, s));
   HG_CUDA_TRY(cudaStreamSynchronize(s));
   return HG_OK;
 }
@@ -295,7 +346,8 @@ int build(hgPlan *p, cudaStream_t s) {
     HG_CUDA_TRY(cudaGetLastError());
     HG_CUDA_TRY(cudaStreamSynchronize(s));
   }
-  return build_fused(p, s);
+  if (int rc = build_fused(p, s)) return rc;
+  return build_pull(p, s);
 }
 
 int inclusive_sum_i32(const int32_t *in, int32_t *out, int64_t n, cudaStream_t s) {
@@ -343,6 +395,9 @@ int hg_plan_destroy(hgPlan *p) {
   cudaFree(p->seg_edge);
   cudaFree(p->seg_slot);
   cudaFree(p->heavy_segs);
+  cudaFree(p->h_ptr);
+  cudaFree(p->h_ind);
+  cudaFree(p->xe);
   cudaFree(p->cflag);
   cudaFree(p->iso_list);
   cudaFree(p->ctrl);

@@ -23,6 +23,12 @@ struct hgPlan {
   int32_t *iso_list = nullptr;    // [niso] vertices in no hyperedge (their Y row is just zero)
   int64_t niso = 0, nexcl = 0;
   int32_t *ctrl = nullptr;        // [nseg + 64] per-call tile counter, give-up flag, block counts, tile flags
+  // pull form (hgef_fused.cu): CSR of H (vertex -> its hyperedges, ascending), built by transposing
+  // the caller's H^T; Xe scratch [num_edges, F] for the hyperedge features between the two phases
+  int32_t *h_ptr = nullptr, *h_ind = nullptr;
+  int32_t max_vdeg = 0;
+  float *xe = nullptr;
+  size_t xe_floats = 0;
   // scratch: partial hyperedge features of heavy hyperedges, [nheavy_edges, F]; L2-resident
   float *scratch = nullptr;
   size_t scratch_floats = 0;

@@ -117,7 +117,9 @@ enum {
   HG_ACCUMULATE = 1,     /* do not zero-fill Y first (reference: torch::zeros, hgnnaggr_cuda.cu:374) */
   HG_FORCE_SCALAR = 4,   /* disable the 128-bit path (testing) */
   HG_TWO_PASS = 8,       /* always memset + segment kernels (the form chosen for small / long-segment graphs) */
-  HG_FORCE_FUSED = 16    /* always the single persistent launch (the form chosen when Y exceeds the L2) */
+  HG_FORCE_FUSED = 16,   /* always the single persistent scatter launch */
+  HG_FORCE_PULL = 32     /* always the gather-only two-phase form (Xe through L2/HBM, no reductions; the form
+                            chosen when Y exceeds the L2 and units are short) */
 };
 
 /* ------------------------------------------------------------------------- *

@@ -19,11 +19,12 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-5
 
 
-@pytest.fixture(params=["auto", "fused", "two_pass"])
+@pytest.fixture(params=["auto", "fused", "two_pass", "pull"])
 def kernel_form(request):
     """Run a test with the library's own choice of kernel form, then with each form forced
     (the persistent kernel is only chosen on its own when Y exceeds the L2)."""
-    ops.DEFAULT_FLAGS = {"auto": 0, "fused": _native.HG_FORCE_FUSED, "two_pass": _native.HG_TWO_PASS}[request.param]
+    ops.DEFAULT_FLAGS = {"auto": 0, "fused": _native.HG_FORCE_FUSED, "two_pass": _native.HG_TWO_PASS,
+                         "pull": _native.HG_FORCE_PULL}[request.param]
     yield request.param
     ops.DEFAULT_FLAGS = 0
 
@@ -145,7 +146,7 @@ def test_plan_sees_heavy_hyperedges_and_schedules_agree(cuda_device):
     want = orc.c_aggr_groups(d["group_key"], d["group_row"], d["group_start"], d["group_end"], d["H_T_colind"],
                              d["X"], s1=d["degE"], a_out=d["degV"])
     assert orc.rel_err(_np(Y1), want) < TOL and orc.rel_err(_np(Y2), want) < TOL
-    for flag in (_native.HG_FORCE_SCALAR, _native.HG_TWO_PASS, _native.HG_FORCE_FUSED):   # scalar tail; both kernel forms
+    for flag in (_native.HG_FORCE_SCALAR, _native.HG_TWO_PASS, _native.HG_FORCE_FUSED, _native.HG_FORCE_PULL):
         Y3 = ops.aggregate(plan, X, s1=hg.degE, a_out=hg.degV, flags=flag)
         assert orc.rel_err(_np(Y3), want) < TOL
     plan.check()
@@ -419,7 +420,7 @@ def test_ragged_and_degenerate_graphs(cuda_device):
             want = orc.c_aggr_formula(ptr, ind, X, s1=_np(hg.degE), a_out=_np(hg.degV))
             out = torch.full((N, F), float("nan"), device=cuda_device)
             plan = ops.get_plan(hg.group_key, hg.group_row, hg.group_start, hg.group_end, hg.H_T_colind, N, hg.num_edges)
-            for flags in (0, _native.HG_TWO_PASS, _native.HG_FORCE_FUSED):
+            for flags in (0, _native.HG_TWO_PASS, _native.HG_FORCE_FUSED, _native.HG_FORCE_PULL):
                 ops.aggregate(plan, X.to(cuda_device), s1=hg.degE, a_out=hg.degV, out=out, flags=flags)
                 assert orc.rel_err(_np(out), want) < TOL or np.abs(want).max() == 0, (len(members), N, ngs, F, flags)
             plan.check()

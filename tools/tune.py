@@ -13,6 +13,7 @@ ap.add_argument("--replicas", type=int, default=64)
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--two-pass", action="store_true")
 ap.add_argument("--force-fused", action="store_true")
+ap.add_argument("--force-pull", action="store_true")
 ap.add_argument("--tag", default="")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
@@ -21,7 +22,7 @@ hg = hgef.HyperGraph(data, dev, data.dataset)
 N, M, Z = hg.num_nodes, hg.num_edges, hg.H_T_colind.numel()
 plan = ops.get_plan(hg.group_key, hg.group_row, hg.group_start, hg.group_end, hg.H_T_colind, N, M)
 W = torch.ones(M, device=dev)
-flags = _native.HG_TWO_PASS if args.two_pass else (_native.HG_FORCE_FUSED if args.force_fused else 0)
+flags = _native.HG_TWO_PASS if args.two_pass else (_native.HG_FORCE_FUSED if args.force_fused else (_native.HG_FORCE_PULL if args.force_pull else 0))
 out = []
 for F in [int(f) for f in args.features.split(",")]:
     X = torch.randn(N, F, device=dev); Y = torch.empty(N, F, device=dev)

@@ -201,6 +201,12 @@ int hg_aggr_groups(int64_t num_nodes, int64_t ngroup, const int32_t *d_key, cons
   return HG_OK;
 }
 
+int hg_plan_launches(const hgPlan *plan, int64_t *kernels) {
+  HG_REQUIRE(plan != nullptr && kernels != nullptr, "plan_launches: NULL argument");
+  *kernels = plan->kernels_launched;
+  return HG_OK;
+}
+
 int hg_plan_check(hgPlan *plan, void *stream) {
   HG_REQUIRE(plan != nullptr, "plan_check: plan is NULL");
   DeviceGuard guard(plan->device);
@@ -231,6 +237,7 @@ int hg_aggr_forward(hgPlan *plan, const float *d_X, const float *d_s1, const flo
   if (pull) {
     Args pa{};
     pa.X = d_X; pa.s1 = d_s1; pa.s2 = d_s2; pa.a_out = d_a_out; pa.a_in = d_a_in; pa.Y = d_Y; pa.F = F;
+    plan->kernels_launched += 2 + (plan->nheavy_segs > 0 ? 1 : 0);
     return launch_pull_any(plan, pa, s);
   }
   const bool fused = vec && !(flags & (HG_ACCUMULATE | HG_TWO_PASS)) && fused_available(plan, F, (flags & HG_FORCE_FUSED) != 0);
@@ -257,6 +264,7 @@ int hg_aggr_forward(hgPlan *plan, const float *d_X, const float *d_s1, const flo
   a.key = plan->key; a.colind = plan->colind; a.seg_edge = plan->seg_edge; a.seg_slot = plan->seg_slot;
   a.X = d_X; a.s1 = d_s1; a.s2 = d_s2; a.a_out = d_a_out; a.a_in = d_a_in; a.Y = d_Y;
   a.scratch = plan->scratch; a.F = F; a.lpr = lanes_per_row(F);
+  plan->kernels_launched += 1 + (plan->nheavy_segs > 0 ? 1 : 0);
   if (fused) return launch_fused(plan, a, s);
   a.nwork = plan->nseg;
   unsigned grid = grid_for(plan->nseg, plan->sm_count, 8);

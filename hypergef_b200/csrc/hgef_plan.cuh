@@ -33,4 +33,5 @@ struct hgPlan {
   float *scratch = nullptr;
   size_t scratch_floats = 0;
   int sm_count = 148;
+  int64_t kernels_launched = 0;   // this library's own kernels launched through the plan (bench.py reports it)
 };

@@ -125,6 +125,12 @@ class Plan:
         self.nseg, self.nheavy_edges, self.nheavy_segs = nseg.value, he.value, hs.value
         self.canonical = bool(canon.value)
 
+    def kernels_launched(self) -> int:
+        """This library's kernels launched through the plan so far (hg_plan_launches)."""
+        n = C.c_int64()
+        _native.call("hg_plan_launches", self.handle, C.byref(n))
+        return n.value
+
     def check(self) -> None:
         """Synchronise and raise if any launch issued with this plan faulted (hg_plan_check)."""
         _native.call("hg_plan_check", self.handle, torch.cuda.current_stream(self.device_index).cuda_stream)

@@ -107,6 +107,9 @@ HG_API int hg_plan_destroy(hgPlan *plan);
 HG_API int hg_plan_info(const hgPlan *plan, int64_t *nseg, int64_t *nheavy_edges,
                         int64_t *nheavy_segs, int32_t *canonical);
 
+/* Number of this library's kernels launched through the plan so far (aggregation calls only). */
+HG_API int hg_plan_launches(const hgPlan *plan, int64_t *kernels);
+
 /* Synchronises `stream` and reports (HG_ECUDA) any fault of the launches issued with this plan,
  * including the fused kernel's bounded-wait give-up.  The reference has no equivalent: it never
  * checks a launch (hgnnaggr_cuda.cu:383-404). */

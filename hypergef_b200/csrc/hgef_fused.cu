@@ -1,30 +1,26 @@
-// hgef_fused.cu -- the single-launch persistent form of the fused aggregation.
+// hgef_fused.cu -- the large-graph forms of the fused aggregation (Y does not fit the L2).
 //
-// Why: on a B200 the two-pass form (cudaMemset Y, then gather/reduce/scatter) moves every Y
-// row through DRAM three times -- zero-fill write, read-modify of the vector reductions,
-// final write-back -- because Y (hundreds of MB) does not survive in the 126 MB L2 between
-// the memset and the kernel.  ncu on the two-pass kernel: 2.08 GB of DRAM traffic + 0.65 GB of
-// memset for 1.31 GB of algorithmic bytes (profiles/).  Here the zero-fill happens INSIDE the
-// kernel, a few microseconds before the first reduction reaches the row, so the zeros are
-// still dirty lines in L2 when `red` hits them and a Y row goes to DRAM exactly once.
+// On a B200 the two-pass form of hgef_aggr.cu (cudaMemset Y, then gather / reduce / scatter) moves
+// every Y row through DRAM three times -- zero-fill write, read-modify of the vector reductions,
+// final write-back -- because Y (hundreds of MB) does not survive in the 126 MB L2 between the
+// memset and the kernel: ncu measured 2.08 GB + 0.65 GB (memset) of DRAM traffic for 1.31 GB of
+// algorithmic bytes.  This file holds the two forms that replace it, plus one kept for A/B:
 //
-// Schedule: CTAs claim TILES of consecutive segments from a global counter (in order).
-//   phase 0  the CTA stages the tile's slice of the flagged column indices, segment bounds,
-//            slots and scales in shared memory (coalesced), and zero-fills the Y rows whose
-//            FIRST occurrence (in H_T_colind order) lies in the tile -- plus its share of
-//            the vertices that are in no hyperedge; then publishes done[tile] and bumps the
-//            finished-tile count of its block of 32 tiles (release).
-//   phase 1  warps take segments of the tile from a shared cursor; gather + reduce in
-//            registers (indices come from shared memory, so the X loads issue immediately).
-//   phase 2  before its first scatter of the tile a warp waits until every tile <= its own has
-//            finished phase 0 (every row it can touch was first-touched by one of those); by
-//            then that is almost always already true, the wait hides behind the gather.  Rows with a single
-//            occurrence in the whole graph are written with plain 128-bit stores (no
-//            zero-fill, no reduction); the rest use red.global.add.v4.f32.
-// Deadlock freedom: a tile id only exists once a RUNNING CTA has claimed it, claims are in
-// order, and phase 0 never waits -- so every tile a waiter depends on completes.
-// Heavy hyperedges (w > 1 segments) publish partial sums to scratch here; the second,
-// small launch (seg_pass2 with the same flags) scatters them.
+//   fused_kernel   persistent SCATTER form (default for F >= 256).  Warps claim small tiles of
+//                  consecutive segments in order; a Y row is zero-filled inside the kernel by the tile
+//                  that touches it first, a few microseconds before the first reduction reaches it, so
+//                  the reductions hit dirty L2 lines and the row goes to DRAM once.  Ordering: publish
+//                  flags per tile + per-32-tile counters, relaxed polls, bounded waits.
+//   pull_kernel    gather-only TWO-PHASE form (default for F <= 128).  L2 reductions are several times
+//                  slower than loads on this part (tools/replay.cu), so phase A writes the hyperedge
+//                  features Xe and phase B gathers them per vertex through the CSR of H: plain stores
+//                  only, every Y row written once, fixed summation order.
+//   pc_kernel      CTA-level tiles with mbarrier producer / consumer warps (HGEF_PC=1; A/B only).
+//
+// All three stream the gathered rows through per-warp cp.async rings in shared memory with the row
+// indices and per-row weights staged one tile ahead, so the only long-latency operations in the hot
+// loops are the 128-bit feature-row copies themselves.  Heavy hyperedges (cut into w > 1 segments by
+// the balancer) combine their partial sums with red.v4 into one row (scratch / Xe).
 #include <cstdlib>
 #include <type_traits>
 

@@ -17,6 +17,8 @@ ap.add_argument("--replicas", type=int, default=1)
 ap.add_argument("--F", type=int, default=256)
 ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--check", type=int, default=1)
+ap.add_argument("--mode", default="partition", choices=["partition", "colshard"],
+                help="partition: vertex/hyperedge blocks + NCCL boundary exchange; colshard: every rank owns F/world feature columns of the whole graph (no collective)")
 args = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 dev = torch.device("cuda", local)
@@ -30,6 +32,37 @@ if args.scale != 1.0:
 data = synth.make_shape(args.shape, replicas=args.replicas, seed=0, device=dev, shape=shape)   # same seed on every rank
 hg = hgef.HyperGraph(data, dev, "synthetic", ngs=shape.ngs)
 N, M, F = hg.num_nodes, hg.num_edges, args.F
+if args.mode == "colshard":
+    Fl = F // world
+    plan = ops.get_plan(hg.group_key, hg.group_row, hg.group_start, hg.group_end, hg.H_T_colind, N, M)
+    gen = torch.Generator(device=dev).manual_seed(5 + rank)
+    Xl = torch.empty(N, Fl, device=dev)
+    for i in range(0, N, 1 << 22):
+        Xl[i:i + (1 << 22)].normal_(generator=gen)
+    Yl = torch.empty_like(Xl)
+    W = torch.ones(M, device=dev)
+    for _ in range(3):
+        ops.aggregate(plan, Xl, s1=hg.degE, s2=W, a_out=hg.degV, out=Yl)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.iters):
+        ops.aggregate(plan, Xl, s1=hg.degE, s2=W, a_out=hg.degV, out=Yl)
+    b.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([a.elapsed_time(b) / args.iters], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    Z = int(hg.H_T_colind.numel())
+    balg = 8 * F * N + world * (4 * Z + 12 * M + 4 * N + 4)
+    if rank == 0:
+        print(json.dumps({"mode": "colshard", "world": world, "N": N, "M": M, "nnz": Z, "F": F, "F_per_rank": Fl,
+                          "ms": ms.item(), "algorithmic_GBps": balg / ms.item() / 1e6}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    sys.exit(0)
 info = build_partition(hg.H_T_csrptr, hg.H_T_colind, N, M, world, rank)
 agg = PartitionedAggregator(info, CudaBackend(dev, shape.ngs))
 gen = torch.Generator(device=dev).manual_seed(5)

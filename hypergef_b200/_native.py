@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("HGEF_B200_LIB") or os.path.join(_HERE, "libhgef_b200.so")   # (override: A/B builds)
 
 HG_OK, HG_EINVAL, HG_ECUDA, HG_ENOMEM, HG_EEMPTY, HG_EGRAPH = range(6)
-HG_ACCUMULATE, HG_FORCE_SCALAR, HG_TWO_PASS, HG_FORCE_FUSED, HG_FORCE_PULL = 1, 4, 8, 16, 32
+HG_ACCUMULATE, HG_FORCE_SCALAR, HG_TWO_PASS, HG_FORCE_FUSED, HG_FORCE_PULL, HG_FORCE_STREAM = 1, 4, 8, 16, 32, 64
 
 
 class HgefBuildError(ImportError):

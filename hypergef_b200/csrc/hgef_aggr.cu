@@ -26,6 +26,9 @@ int launch_fused(hgPlan *plan, const dev::Args &base, cudaStream_t s);
 int fused_check(hgPlan *plan, cudaStream_t s);
 bool pull_available(const hgPlan *plan, int F, bool force);
 int launch_pull_any(hgPlan *plan, const dev::Args &base, cudaStream_t s);
+bool stream_available(const hgPlan *plan, int F, bool force);
+int launch_stream(hgPlan *plan, const dev::Args &base, cudaStream_t s);
+int stream_check(hgPlan *plan, cudaStream_t s);
 namespace {
 using namespace dev;
 
@@ -214,6 +217,7 @@ int hg_plan_check(hgPlan *plan, void *stream) {
   cudaStream_t s = (cudaStream_t)stream;
   HG_CUDA_TRY(cudaStreamSynchronize(s));
   HG_CUDA_TRY(cudaGetLastError());
+  if (int rc = stream_check(plan, s)) return rc;
   return fused_check(plan, s);
 }
 
@@ -229,7 +233,16 @@ int hg_aggr_forward(hgPlan *plan, const float *d_X, const float *d_s1, const flo
   DeviceGuard guard(plan->device);
   HG_REQUIRE(guard.ok(), "aggr_forward: cannot select device %d", plan->device);
   cudaStream_t s = (cudaStream_t)stream;
-  const bool vec = F % 4 == 0 && F <= 512 && !(flags & HG_FORCE_SCALAR) && aligned16(d_X) && aligned16(d_Y);
+  const bool vec4 = F % 4 == 0 && !(flags & HG_FORCE_SCALAR) && aligned16(d_X) && aligned16(d_Y);
+  const bool vec = vec4 && F <= 512;
+  // stream form: both stages as lean row streams, one persistent launch (hgef_stream.cu)
+  const bool use_stream = vec4 && !(flags & (HG_ACCUMULATE | HG_TWO_PASS | HG_FORCE_FUSED | HG_FORCE_PULL)) &&
+                      stream_available(plan, F, (flags & HG_FORCE_STREAM) != 0);
+  if (use_stream) {
+    Args pa{};
+    pa.X = d_X; pa.s1 = d_s1; pa.s2 = d_s2; pa.a_out = d_a_out; pa.a_in = d_a_in; pa.Y = d_Y; pa.F = F;
+    return launch_stream(plan, pa, s);
+  }
   // single-launch persistent form: zero-fill happens inside the kernel (hgef_fused.cu)
   // gather-only two-phase form (no reductions): the fastest when it applies (hgef_fused.cu)
   const bool pull = vec && !(flags & (HG_ACCUMULATE | HG_TWO_PASS | HG_FORCE_FUSED)) &&

@@ -17,6 +17,8 @@
 #include "hgef_plan.cuh"
 
 namespace hg {
+int build_stream(hgPlan *p, cudaStream_t s);
+void stream_free(hgPlan *p);
 namespace {
 
 enum : int { kBadIndex = 1, kBadKey = 2, kBadGroup = 4, kNotCanonical = 8 };
@@ -347,7 +349,8 @@ int build(hgPlan *p, cudaStream_t s) {
     HG_CUDA_TRY(cudaStreamSynchronize(s));
   }
   if (int rc = build_fused(p, s)) return rc;
-  return build_pull(p, s);
+  if (int rc = build_pull(p, s)) return rc;
+  return build_stream(p, s);
 }
 
 int inclusive_sum_i32(const int32_t *in, int32_t *out, int64_t n, cudaStream_t s) {
@@ -402,6 +405,7 @@ int hg_plan_destroy(hgPlan *p) {
   cudaFree(p->iso_list);
   cudaFree(p->ctrl);
   cudaFree(p->scratch);
+  stream_free(p);
   delete p;
   return HG_OK;
 }

@@ -29,6 +29,23 @@ struct hgPlan {
   int32_t max_vdeg = 0;
   float *xe = nullptr;
   size_t xe_floats = 0;
+  // stream form (hgef_stream.cu): row programs of the two stages, base runs, stage-B vertex order
+  int32_t *st_srcA = nullptr, *st_dstA = nullptr, *st_runA = nullptr;
+  int32_t *st_srcB = nullptr, *st_dstB = nullptr, *st_needB = nullptr, *st_runB = nullptr;
+  int32_t *st_perm = nullptr;     // [N] vertices ordered by their last hyperedge; the tail holds the isolated ones
+  int32_t *st_ctrl = nullptr;     // ticket counters of the two-launch form
+  int32_t *st_last_ctrl = nullptr;
+  int64_t st_nrunA = 0, st_nrunB = 0, st_nunitB = 0, st_niso = 0;
+  int32_t st_ready = 0;
+  struct StreamSched {            // fused ticket order for one item size / lag
+    int bpi, lag, nslab;
+    int32_t GA, GB, nblk;
+    int2 *sched;
+    int32_t *ctrl;
+  };
+  static constexpr int kMaxSched = 8;
+  StreamSched st_sched[kMaxSched];
+  int st_nsched = 0;
   // scratch: partial hyperedge features of heavy hyperedges, [nheavy_edges, F]; L2-resident
   float *scratch = nullptr;
   size_t scratch_floats = 0;

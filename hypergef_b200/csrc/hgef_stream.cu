@@ -1,0 +1,683 @@
+// hgef_stream.cu -- the STREAM form of the fused aggregation: both stages as lean row streams,
+// optionally in ONE persistent launch with the hyperedge features handed over through the L2.
+//
+// What the round-1 profiles said (profiles/r01_ncu_prof_r1_pull_f128.txt): the gather-only two-phase
+// form has ideal DRAM traffic but spends ~45 warp instructions per gathered row (tile staging in
+// shared memory, cp.async ring, per-unit bookkeeping for units of 2-4 rows) at 16 resident warps per
+// SM: issue-bound at half the DRAM rate.  A trivially lean gather of the same address stream
+// saturates DRAM once >= 128 KB of row loads are in flight per SM (tools/replay.cu).
+//
+// Here everything a row needs is precomputed once per graph into a ROW PROGRAM (hg_plan_create):
+//     src[p]  row to gather at position p, bit31 = "last member of its unit"
+//     dst[p]  output row of the unit that owns p, bit31 = "heavy: reduce, do not store"
+//     run[r]  first position of base run r (unit-aligned, ~kL0 positions each)
+// for stage A (units = balancer segments of H^T, gather X, output Xe) and stage B (units = vertices,
+// gather Xe, output Y).  A sub-warp of SW lanes streams one run: 32 positions' src/dst words are
+// held one per lane and handed out by shuffles, kVec 128-bit row loads per lane are issued
+// back to back straight into registers (no shared memory at all), and a unit end costs one scale and
+// one 128-bit store per lane.  ~12-15 warp instructions per row, 24-32 resident warps per SM.
+//
+// FUSED launch: stage-B units are ordered by the LAST hyperedge they depend on, both stages are cut
+// into items and merged into one ticket sequence in which a B item follows the A items it needs
+// (plus a lag); warps claim tickets in order from one counter, A items publish per-block completion
+// counts (release), B items wait on a monotone per-warp watermark (normally already satisfied).
+// Xe rows are therefore consumed while still L2-resident, the Xe read never reaches DRAM, and there
+// is no ramp-down / ramp-up between the stages.  Deadlock-free: an item is only claimed by a running
+// warp, tickets are claimed in order, a B item waits only for A items with smaller tickets, A items
+// never wait; waits are bounded (give-up flag -> hg_plan_check).
+// Wide rows are processed as column SLABS (the ticket sequence repeated per slab) so that the set of
+// rows in flight, in bytes, stays below the L2 size.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <cstdlib>
+
+#include "hgef_aggr.cuh"
+
+namespace hg {
+namespace {
+using namespace dev;
+
+constexpr uint32_t kEnd = 0x80000000u, kRowMask = 0x7fffffffu;
+constexpr int kL0 = 16;      // positions per base run
+constexpr int kBlk = 8;      // A items per completion counter
+constexpr int kVec = 8;      // 128-bit row loads in flight per lane
+constexpr int kCtrlHdr = 8;  // ctrl[0] ticket counter, ctrl[1] give-up flag, ctrl[8..] block counts per slab
+
+struct StreamArgs {
+  const int32_t *src[2], *dst[2], *run[2];   // row programs: [0] stage A, [1] stage B
+  const float *in[2];
+  float *out[2];
+  const float *w_in[2], *w_o1[2], *w_o2[2];  // gather-side weight per source row; output scales per output row
+  int32_t nrun0[2];                          // base runs
+  const int2 *sched;                         // fused: {item << 1 | stage, #completion blocks needed}
+  int32_t *ctrl;
+  const int32_t *iso;                        // vertices in no hyperedge: Y row = 0
+  int32_t niso;
+  int32_t nitem;                             // tickets per slab
+  int32_t nslab, slabF;                      // column slabs of slabF floats
+  int32_t F;                                 // row stride (floats)
+  int32_t k0;                                // base runs per sub-warp run
+  int32_t stage;                             // unfused: the stage this launch runs
+  int32_t nblk, GA;                          // fused: completion blocks per slab, A items
+  int32_t y_stream;                          // stage-B output stores carry the streaming (evict-first) hint
+};
+
+__device__ __forceinline__ int ld_relaxed_i32(const int *p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_inc_relaxed(int *p) {
+  asm volatile("red.relaxed.gpu.global.add.s32 [%0], 1;" ::"l"(p) : "memory");
+}
+// row loads.  Fused launches read rows written earlier in the SAME launch: L2-coherent loads
+// (no L1 allocation), volatile so that they stay behind the acquire fence of the wait.
+template <bool CG>
+__device__ __forceinline__ float4 ld_row16(const float *p) {
+  if (CG) {
+    float4 v;
+    asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+  }
+  return __ldg(reinterpret_cast<const float4 *>(p));
+}
+__device__ __forceinline__ void st_row16(float *p, float4 v) {
+  asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_row16_stream(float *p, float4 v) {   // written once, never re-read
+  asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+template <int SW, int VPL>
+struct SGeo {
+  static constexpr int kSub = 32 / SW;                          // row streams per warp
+  static constexpr int kU = (kVec / VPL) < SW ? (kVec / VPL) : SW;   // rows in flight per stream
+  static constexpr int kStride = SW * 4;                        // floats between a lane's vectors
+};
+
+template <int SW, int VPL, bool HAS_WIN, bool FUSED, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) stream_kernel(const StreamArgs sa) {
+  using G = SGeo<SW, VPL>;
+  constexpr int U = G::kU;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / SW, sl = lane % SW;
+  const int col = sl * 4;
+  const int F = sa.F;
+  const uint32_t row_bytes = (uint32_t)F * 4u;
+  const int total = sa.nitem * sa.nslab;
+  int blk_wm = 0, wm_slab = 0;
+
+  for (;;) {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(sa.ctrl, 1);
+    t = __shfl_sync(kFull, t, 0);
+    if (t >= total) break;
+    const int slab = sa.nslab > 1 ? t / sa.nitem : 0;
+    const int k = t - slab * sa.nitem;
+    const int col0 = slab * sa.slabF;
+    const int Fs = min(sa.slabF, F - col0);
+    int stage = sa.stage, gid = k, need = 0;
+    if (FUSED) {
+      const int2 s = __ldg(sa.sched + k);
+      stage = s.x & 1;
+      gid = s.x >> 1;
+      need = s.y;
+    }
+    // column mask of this lane's vectors; a masked vector LOADS column 0 of the slab instead (no branch
+    // around the load) and is never stored
+    bool ok[VPL];
+    int off[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      ok[v] = col + v * G::kStride < Fs;
+      off[v] = ok[v] ? col + v * G::kStride : 0;
+    }
+
+    // this ticket's share of the vertices that no hyperedge touches (only the B side has any)
+    if (sa.niso > 0 && (FUSED || stage == 1)) {
+      const int i0 = (int)((int64_t)sa.niso * k / sa.nitem), i1 = (int)((int64_t)sa.niso * (k + 1) / sa.nitem);
+      for (int i = i0 + sub; i < i1; i += G::kSub) {
+        float *yp = sa.out[1] + (int64_t)__ldg(sa.iso + i) * F + col0;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v)
+          if (ok[v]) st_row16_stream(yp + off[v], make_float4(0.f, 0.f, 0.f, 0.f));
+      }
+    }
+
+    const int32_t *__restrict__ src = sa.src[stage];
+    const int32_t *__restrict__ dst = sa.dst[stage];
+    const float *in = sa.in[stage] + col0;
+    float *out = sa.out[stage] + col0;
+    const float *__restrict__ w_in = sa.w_in[stage];
+    const float *__restrict__ w_o1 = sa.w_o1[stage];
+    const float *__restrict__ w_o2 = sa.w_o2[stage];
+    const int nrun0 = sa.nrun0[stage];
+    const int64_t r0 = ((int64_t)gid * G::kSub + sub) * sa.k0;
+    const int32_t ps = __ldg(sa.run[stage] + min(r0, (int64_t)nrun0));
+    const int32_t pe = __ldg(sa.run[stage] + min(r0 + sa.k0, (int64_t)nrun0));
+
+    if (FUSED && stage == 1 && need > 0) {
+      // all A items of completion blocks [0, need) of this slab must be published
+      if (slab != wm_slab) { wm_slab = slab; blk_wm = 0; }
+      if (blk_wm < need) {
+        const int *cnt = sa.ctrl + kCtrlHdr + (int64_t)slab * sa.nblk;
+        unsigned spins = 0;
+        while (blk_wm < need) {
+          const int b = blk_wm + lane;
+          bool done = true;
+          if (b < need) done = ld_relaxed_i32(cnt + b) == min(kBlk, sa.GA - b * kBlk);
+          const unsigned m = __ballot_sync(kFull, done);
+          blk_wm = min(need, blk_wm + (m == kFull ? 32 : __ffs(~m) - 1));
+          if (blk_wm < need && m != kFull) {
+            __nanosleep(64);
+            // bounded: a protocol bug must not hang the GPU; once one item gave up, nobody waits any more
+            ++spins;
+            if (spins > (1u << 20) || ((spins & 255u) == 0 && ld_relaxed_i32(sa.ctrl + 1) != 0)) {
+              if (lane == 0) atomicExch(sa.ctrl + 1, 1);
+              break;
+            }
+          }
+        }
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      }
+    }
+
+    // ---- stream the run: chunks of SW positions, their src/dst words one per lane ----
+    float4 acc[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int32_t cb = ps;
+    uint32_t c_src = 0, c_dst = 0;
+    if (cb + sl < pe) {
+      c_src = (uint32_t)__ldg(src + cb + sl);
+      c_dst = (uint32_t)__ldg(dst + cb + sl);
+    }
+    while (__any_sync(kFull, cb < pe)) {
+      float c_w = 1.0f, c_sc = 1.0f;
+      if (cb + sl < pe) {
+        if (HAS_WIN && w_in) c_w = __ldg(w_in + (c_src & kRowMask));
+        if (c_src & kEnd) {
+          const uint32_t orow = c_dst & kRowMask;
+          if (w_o1) c_sc = __ldg(w_o1 + orow);
+          if (w_o2) c_sc *= __ldg(w_o2 + orow);
+        }
+      }
+      uint32_t n_src = 0, n_dst = 0;   // next chunk's words: in flight while this chunk streams
+      if (cb + SW + sl < pe) {
+        n_src = (uint32_t)__ldg(src + cb + SW + sl);
+        n_dst = (uint32_t)__ldg(dst + cb + SW + sl);
+      }
+#pragma unroll 1
+      for (int b = 0; b < SW; b += U) {
+        if (!__any_sync(kFull, cb + b < pe)) break;
+        float4 x[U][VPL];
+        uint32_t id[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          // (positions past the end of the run carry src word 0: row 0 is loaded and ignored)
+          id[u] = __shfl_sync(kFull, c_src, b + u, SW);
+          const uint64_t rb = (uint64_t)(id[u] & kRowMask) * row_bytes;   // one IMAD.WIDE.U32
+#pragma unroll
+          for (int v = 0; v < VPL; ++v)
+            x[u][v] = ld_row16<FUSED>(reinterpret_cast<const float *>(reinterpret_cast<const char *>(in + off[v]) + rb));
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          // Positions past the end of the run gathered row 0 and carry no END flag: what they add to
+          // `acc` is never stored (a run ends with an END, and `acc` restarts from zero per item).
+          float w = 1.0f;
+          if (HAS_WIN) w = __shfl_sync(kFull, c_w, b + u, SW);
+          const bool end = (id[u] & kEnd) != 0;
+          uint32_t d = 0;
+          float sc = 1.0f;
+          if (SW < 32 || end) {   // (a whole-warp stream branches uniformly; sub-warps shuffle unconditionally)
+            d = __shfl_sync(kFull, c_dst, b + u, SW);
+            sc = __shfl_sync(kFull, c_sc, b + u, SW);
+          }
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) {
+            if (HAS_WIN) {
+              acc[v].x = fmaf(w, x[u][v].x, acc[v].x);
+              acc[v].y = fmaf(w, x[u][v].y, acc[v].y);
+              acc[v].z = fmaf(w, x[u][v].z, acc[v].z);
+              acc[v].w = fmaf(w, x[u][v].w, acc[v].w);
+            } else {
+              acc[v].x += x[u][v].x;
+              acc[v].y += x[u][v].y;
+              acc[v].z += x[u][v].z;
+              acc[v].w += x[u][v].w;
+            }
+          }
+          if (end) {   // unit complete: one output row
+            char *op = reinterpret_cast<char *>(out) + (uint64_t)(d & kRowMask) * row_bytes;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+              if (ok[v]) {
+                const float4 r = make_float4(acc[v].x * sc, acc[v].y * sc, acc[v].z * sc, acc[v].w * sc);
+                float *o = reinterpret_cast<float *>(op) + off[v];
+                if (d & kEnd) red_add_v4(o, r);
+                else if (stage == 1 && sa.y_stream) st_row16_stream(o, r);
+                else st_row16(o, r);
+              }
+              acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+        }
+      }
+      cb += SW;
+      c_src = n_src;
+      c_dst = n_dst;
+    }
+
+    if (FUSED && stage == 0) {   // publish: this item's Xe rows are complete
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        red_inc_relaxed(sa.ctrl + kCtrlHdr + (int64_t)slab * sa.nblk + gid / kBlk);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Row-program construction (once per graph)
+// ------------------------------------------------------------------------------------------
+#define GRID(n) (unsigned)ceil_div<int64_t>((n), 256), 256
+
+// one warp per unit: src = gathered row (| END on the unit's last position), dst = output row (| HEAVY)
+__global__ void prog_fill_kernel(int64_t nunit, const int32_t *__restrict__ ptr_in,    // where the unit's members are
+                                 const int32_t *__restrict__ ptr_out,                  // where they go (may alias)
+                                 const int32_t *__restrict__ unit_of,                  // optional: source unit of slot i
+                                 const int32_t *__restrict__ ind, const int32_t *__restrict__ out_row,
+                                 const int32_t *__restrict__ heavy_slot, const int32_t *__restrict__ unit_need,
+                                 int32_t *__restrict__ src, int32_t *__restrict__ dst, int32_t *__restrict__ need) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (i >= nunit) return;
+  const int32_t u = unit_of ? unit_of[i] : (int32_t)i;
+  const int32_t a = ptr_in[u], n = ptr_in[u + 1] - a, o = ptr_out[i];
+  uint32_t d = (uint32_t)(out_row ? out_row[u] : u);
+  if (heavy_slot && heavy_slot[u] >= 0) d |= kEnd;
+  const int32_t nd = unit_need ? unit_need[i] : 0;
+  for (int32_t j = lane; j < n; j += 32) {
+    uint32_t s = (uint32_t)ind[a + j];
+    if (j == n - 1) s |= kEnd;
+    src[o + j] = (int32_t)s;
+    dst[o + j] = (int32_t)d;
+    if (need) need[o + j] = nd;
+  }
+}
+
+// run[r] = smallest unit start >= r * kL0 (units are never cut); run[nrun] = npos
+__global__ void run_ptr_kernel(int64_t nrun, int64_t nunit, const int32_t *__restrict__ ptr, int64_t npos,
+                               int32_t *__restrict__ run) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r > nrun) return;
+  if (r == nrun) { run[r] = (int32_t)npos; return; }
+  const int64_t target = r * kL0;
+  int64_t lo = 0, hi = nunit;          // first unit index with ptr[idx] >= target (ptr[nunit] = npos >= target)
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (ptr[mid] < target) lo = mid + 1; else hi = mid;
+  }
+  run[r] = ptr[lo];
+}
+
+// last position (exclusive) of every hyperedge in the stage-A order
+__global__ void edge_end_kernel(int64_t nseg, const int32_t *__restrict__ key, const int32_t *__restrict__ seg_edge,
+                                int32_t *__restrict__ edge_end) {
+  const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (s >= nseg) return;
+  if (s + 1 == nseg || seg_edge[s + 1] != seg_edge[s]) edge_end[seg_edge[s]] = key[s + 1];
+}
+
+// sort key of a vertex: its last hyperedge (isolated vertices: M, they go to the end)
+__global__ void vertex_key_kernel(int64_t n, const int32_t *__restrict__ h_ptr, const int32_t *__restrict__ h_ind,
+                                  int32_t m, int32_t *__restrict__ keys, int32_t *__restrict__ ids) {
+  const int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  keys[v] = h_ptr[v + 1] > h_ptr[v] ? h_ind[h_ptr[v + 1] - 1] : m;
+  ids[v] = (int32_t)v;
+}
+
+__global__ void perm_deg_kernel(int64_t nb, const int32_t *__restrict__ perm, const int32_t *__restrict__ keys_sorted,
+                                const int32_t *__restrict__ h_ptr, const int32_t *__restrict__ edge_end,
+                                int32_t *__restrict__ deg, int32_t *__restrict__ unit_need) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i > nb) return;
+  if (i == nb) { deg[i] = 0; return; }
+  const int32_t v = perm[i];
+  deg[i] = h_ptr[v + 1] - h_ptr[v];
+  unit_need[i] = edge_end[keys_sorted[i]];
+}
+
+// number of vertices with at least one hyperedge = index after the last sorted key < M
+__global__ void count_units_kernel(int64_t n, const int32_t *__restrict__ keys_sorted, int32_t m, int32_t *__restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n && keys_sorted[i] < m && (i + 1 == n || keys_sorted[i + 1] >= m)) *out = (int32_t)(i + 1);
+}
+
+// ---- fused schedule for one (items of `bpi` base runs, lag) configuration ----
+// a_after[gb] = number of A items that precede B item gb in the ticket order
+__global__ void sched_b_kernel(int32_t GB, int32_t GA, int32_t bpi, int32_t lag, const int32_t *__restrict__ runA,
+                               int32_t nrunA, const int32_t *__restrict__ runB, int32_t nrunB,
+                               const int32_t *__restrict__ needB, int32_t *__restrict__ a_after,
+                               int32_t *__restrict__ need_blk) {
+  const int32_t gb = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gb >= GB) return;
+  const int32_t p0 = runB[min((int64_t)gb * bpi, (int64_t)nrunB)], p1 = runB[min(((int64_t)gb + 1) * bpi, (int64_t)nrunB)];
+  (void)p0;
+  int32_t cnt = 0;   // A items [0, cnt) must be complete
+  // An item can be empty (a unit longer than an item spills over the following ones).  The need is taken
+  // from the last position at or before the item's end in every case, so that it is monotone in gb --
+  // the merge below relies on that.
+  if (p1 > 0) {
+    const int32_t npos = needB[p1 - 1];   // stage-A positions [0, npos) must be complete
+    if (npos > 0) {
+      int32_t lo = 0, hi = GA;   // first A item whose end position >= npos
+      while (lo < hi) {
+        const int32_t mid = (lo + hi) >> 1;
+        const int32_t endp = runA[min(((int64_t)mid + 1) * bpi, (int64_t)nrunA)];
+        if (endp < npos) lo = mid + 1; else hi = mid;
+      }
+      cnt = min(lo + 1, GA);
+    }
+  }
+  const int32_t nb = (cnt + kBlk - 1) / kBlk;
+  need_blk[gb] = nb;
+  a_after[gb] = cnt == 0 ? 0 : min(GA, nb * kBlk + lag);
+}
+
+__global__ void sched_merge_kernel(int32_t GA, int32_t GB, const int32_t *__restrict__ a_after,
+                                   const int32_t *__restrict__ need_blk, int2 *__restrict__ sched) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < GB) sched[i + a_after[i]] = make_int2((i << 1) | 1, need_blk[i]);
+  if (i < GA) {   // B items with a_after <= i come first
+    int32_t lo = 0, hi = GB;
+    while (lo < hi) {
+      const int32_t mid = (lo + hi) >> 1;
+      if (a_after[mid] <= i) lo = mid + 1; else hi = mid;
+    }
+    sched[i + lo] = make_int2(i << 1, 0);
+  }
+}
+
+__global__ void zero_rows_kernel(int64_t nrows, const int32_t *__restrict__ segs, const int32_t *__restrict__ seg_edge,
+                                 float *__restrict__ xe, int F) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (w >= nrows) return;
+  float *row = xe + (int64_t)seg_edge[segs[w]] * F;
+  for (int c = lane; c < F; c += 32) row[c] = 0.0f;
+}
+
+template <typename T>
+int dev_alloc(T **p, size_t n) {
+  if (cudaMalloc((void **)p, (n ? n : 1) * sizeof(T)) != cudaSuccess) {
+    cudaGetLastError();
+    return set_error(HG_ENOMEM, "stream plan: cannot allocate %zu bytes", n * sizeof(T));
+  }
+  return HG_OK;
+}
+
+int env_int(const char *name, int dflt) {
+  const char *v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
+}  // namespace
+
+void stream_free(hgPlan *p) {
+  cudaFree(p->st_srcA); cudaFree(p->st_dstA); cudaFree(p->st_runA);
+  cudaFree(p->st_srcB); cudaFree(p->st_dstB); cudaFree(p->st_needB); cudaFree(p->st_runB);
+  cudaFree(p->st_perm); cudaFree(p->st_ctrl);
+  for (int i = 0; i < p->st_nsched; ++i) { cudaFree(p->st_sched[i].sched); cudaFree(p->st_sched[i].ctrl); }
+  p->st_nsched = 0;
+}
+
+// Builds the two row programs.  Needs the canonical segment schedule and H (build_pull).
+int build_stream(hgPlan *p, cudaStream_t s) {
+  const int64_t N = p->num_nodes, M = p->num_edges, Z = p->nnz, S = p->nseg;
+  if (!p->canonical || p->h_ptr == nullptr || Z == 0) return HG_OK;
+  {   // the segments must tile [0, Z) exactly (the balancer's do)
+    int32_t k0 = -1, kS = -1;
+    HG_CUDA_TRY(cudaMemcpyAsync(&k0, p->key, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    HG_CUDA_TRY(cudaMemcpyAsync(&kS, p->key + S, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    HG_CUDA_TRY(cudaStreamSynchronize(s));
+    if (k0 != 0 || kS != Z) return HG_OK;
+  }
+  // stage A: units = balancer segments in order
+  if (int rc = dev_alloc(&p->st_srcA, Z)) return rc;
+  if (int rc = dev_alloc(&p->st_dstA, Z)) return rc;
+  p->st_nrunA = ceil_div<int64_t>(Z, kL0);
+  if (int rc = dev_alloc(&p->st_runA, p->st_nrunA + 1)) return rc;
+  prog_fill_kernel<<<(unsigned)ceil_div<int64_t>(S * 32, 256), 256, 0, s>>>(
+      S, p->key, p->key, nullptr, p->colind, p->seg_edge, p->seg_slot, nullptr, p->st_srcA, p->st_dstA, nullptr);
+  run_ptr_kernel<<<GRID(p->st_nrunA + 1), 0, s>>>(p->st_nrunA, S, p->key, Z, p->st_runA);
+  HG_CUDA_TRY(cudaGetLastError());
+
+  // stage B: units = vertices, ordered by their last hyperedge (the stage-A position they wait for)
+  DevBuf<int32_t> keys, ids, keys_s, edge_end, deg, ptrB, unit_need;
+  HG_CUDA_TRY(keys.alloc(N)); HG_CUDA_TRY(ids.alloc(N)); HG_CUDA_TRY(keys_s.alloc(N));
+  HG_CUDA_TRY(edge_end.alloc(M + 1)); HG_CUDA_TRY(deg.alloc(N + 1)); HG_CUDA_TRY(ptrB.alloc(N + 1));
+  HG_CUDA_TRY(unit_need.alloc(N));
+  if (int rc = dev_alloc(&p->st_perm, N)) return rc;
+  HG_CUDA_TRY(cudaMemsetAsync(edge_end.p, 0, (size_t)(M + 1) * sizeof(int32_t), s));
+  edge_end_kernel<<<GRID(S), 0, s>>>(S, p->key, p->seg_edge, edge_end.p);
+  vertex_key_kernel<<<GRID(N), 0, s>>>(N, p->h_ptr, p->h_ind, (int32_t)M, keys.p, ids.p);
+  HG_CUDA_TRY(cudaGetLastError());
+  int end_bit = 1;
+  while (end_bit < 32 && (int64_t(1) << end_bit) <= M) ++end_bit;
+  size_t bytes = 0;
+  HG_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys.p, keys_s.p, ids.p, p->st_perm, N, 0, end_bit, s));
+  {
+    DevBuf<char> ws;
+    HG_CUDA_TRY(ws.alloc(bytes));
+    HG_CUDA_TRY(cub::DeviceRadixSort::SortPairs(ws.p, bytes, keys.p, keys_s.p, ids.p, p->st_perm, N, 0, end_bit, s));
+    HG_CUDA_TRY(cudaStreamSynchronize(s));
+  }
+  perm_deg_kernel<<<GRID(N + 1), 0, s>>>(N, p->st_perm, keys_s.p, p->h_ptr, edge_end.p, deg.p, unit_need.p);
+  HG_CUDA_TRY(cudaGetLastError());
+  {
+    size_t b2 = 0;
+    HG_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, b2, deg.p, ptrB.p, N + 1, s));
+    DevBuf<char> ws;
+    HG_CUDA_TRY(ws.alloc(b2));
+    HG_CUDA_TRY(cub::DeviceScan::ExclusiveSum(ws.p, b2, deg.p, ptrB.p, N + 1, s));
+    HG_CUDA_TRY(cudaStreamSynchronize(s));
+  }
+  // isolated vertices are the tail of the permutation (sorted key == M)
+  {
+    DevBuf<int32_t> nb;
+    HG_CUDA_TRY(nb.alloc(1));
+    HG_CUDA_TRY(cudaMemsetAsync(nb.p, 0, sizeof(int32_t), s));
+    count_units_kernel<<<GRID(N), 0, s>>>(N, keys_s.p, (int32_t)M, nb.p);
+    int32_t h_nb = 0;
+    HG_CUDA_TRY(cudaMemcpyAsync(&h_nb, nb.p, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    HG_CUDA_TRY(cudaStreamSynchronize(s));
+    p->st_nunitB = h_nb;
+    p->st_niso = N - h_nb;
+  }
+  if (int rc = dev_alloc(&p->st_srcB, Z)) return rc;
+  if (int rc = dev_alloc(&p->st_dstB, Z)) return rc;
+  if (int rc = dev_alloc(&p->st_needB, Z)) return rc;
+  p->st_nrunB = ceil_div<int64_t>(Z, kL0);
+  if (int rc = dev_alloc(&p->st_runB, p->st_nrunB + 1)) return rc;
+  if (int rc = dev_alloc(&p->st_ctrl, 2 * kCtrlHdr)) return rc;
+  const int64_t NB = p->st_nunitB;
+  if (NB > 0)
+    prog_fill_kernel<<<(unsigned)ceil_div<int64_t>(NB * 32, 256), 256, 0, s>>>(
+        NB, p->h_ptr, ptrB.p, p->st_perm, p->h_ind, nullptr, nullptr, unit_need.p, p->st_srcB, p->st_dstB, p->st_needB);
+  run_ptr_kernel<<<GRID(p->st_nrunB + 1), 0, s>>>(p->st_nrunB, NB, ptrB.p, Z, p->st_runB);
+  HG_CUDA_TRY(cudaGetLastError());
+  HG_CUDA_TRY(cudaStreamSynchronize(s));
+  p->st_ready = 1;
+  return HG_OK;
+}
+
+namespace {
+
+// schedule (and control words) for items of `bpi` base runs; cached in the plan
+int get_sched(hgPlan *p, int bpi, int lag, int nslab, cudaStream_t s, hgPlan::StreamSched **out) {
+  for (int i = 0; i < p->st_nsched; ++i) {
+    hgPlan::StreamSched &c = p->st_sched[i];
+    if (c.bpi == bpi && c.lag == lag && c.nslab >= nslab) { *out = &c; return HG_OK; }
+  }
+  if (p->st_nsched == hgPlan::kMaxSched) {   // recycle the oldest entry
+    HG_CUDA_TRY(cudaStreamSynchronize(s));
+    cudaFree(p->st_sched[0].sched); cudaFree(p->st_sched[0].ctrl);
+    for (int i = 1; i < p->st_nsched; ++i) p->st_sched[i - 1] = p->st_sched[i];
+    --p->st_nsched;
+  }
+  hgPlan::StreamSched c{};
+  c.bpi = bpi; c.lag = lag; c.nslab = nslab;
+  c.GA = (int32_t)ceil_div<int64_t>(p->st_nrunA, bpi);
+  c.GB = (int32_t)ceil_div<int64_t>(p->st_nrunB, bpi);
+  c.nblk = (c.GA + kBlk - 1) / kBlk;
+  if (int rc = dev_alloc(&c.sched, (size_t)c.GA + c.GB)) return rc;
+  if (int rc = dev_alloc(&c.ctrl, (size_t)kCtrlHdr + (size_t)c.nblk * nslab)) return rc;
+  DevBuf<int32_t> a_after, need_blk;
+  HG_CUDA_TRY(a_after.alloc(c.GB)); HG_CUDA_TRY(need_blk.alloc(c.GB));
+  sched_b_kernel<<<GRID(c.GB), 0, s>>>(c.GB, c.GA, bpi, lag, p->st_runA, (int32_t)p->st_nrunA, p->st_runB,
+                                      (int32_t)p->st_nrunB, p->st_needB, a_after.p, need_blk.p);
+  const int32_t gmax = c.GA > c.GB ? c.GA : c.GB;
+  sched_merge_kernel<<<GRID(gmax), 0, s>>>(c.GA, c.GB, a_after.p, need_blk.p, c.sched);
+  HG_CUDA_TRY(cudaGetLastError());
+  HG_CUDA_TRY(cudaStreamSynchronize(s));
+  p->st_sched[p->st_nsched] = c;
+  *out = &p->st_sched[p->st_nsched++];
+  return HG_OK;
+}
+
+struct StreamCfg {
+  int sw, vpl, slabF, nslab, k0, ctas, lag, occ;
+  bool fused;
+};
+
+template <int SW, int VPL, bool HAS_WIN, bool FUSED>
+int launch_one(hgPlan *p, StreamArgs &sa, const StreamCfg &cfg, cudaStream_t s) {
+  auto kern = cfg.occ == 4 ? stream_kernel<SW, VPL, HAS_WIN, FUSED, 4> : stream_kernel<SW, VPL, HAS_WIN, FUSED, 3>;
+  int per_sm = 0;
+  HG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0));
+  if (per_sm < 1) per_sm = 1;
+  if (cfg.ctas > 0 && cfg.ctas < per_sm) per_sm = cfg.ctas;
+  int64_t grid = (int64_t)p->sm_count * per_sm;
+  const int64_t useful = ceil_div<int64_t>((int64_t)sa.nitem * sa.nslab, kWarpsPerBlock);
+  if (grid > useful) grid = useful;
+  if (grid < 1) grid = 1;
+  kern<<<(unsigned)grid, kThreads, 0, s>>>(sa);
+  HG_CUDA_TRY(cudaGetLastError());
+  return HG_OK;
+}
+
+template <bool HAS_WIN, bool FUSED>
+int dispatch_geo(hgPlan *p, StreamArgs &sa, const StreamCfg &cfg, cudaStream_t s) {
+#define HG_CASE(SW_, VPL_) \
+  if (cfg.sw == SW_ && cfg.vpl == VPL_) return launch_one<SW_, VPL_, HAS_WIN, FUSED>(p, sa, cfg, s)
+  HG_CASE(4, 1); HG_CASE(8, 1); HG_CASE(16, 1); HG_CASE(32, 1); HG_CASE(32, 2); HG_CASE(32, 4);
+#undef HG_CASE
+  return set_error(HG_EINVAL, "stream: no kernel for sub-warp %d x %d vectors", cfg.sw, cfg.vpl);
+}
+
+int dispatch(hgPlan *p, StreamArgs &sa, const StreamCfg &cfg, bool has_win, cudaStream_t s) {
+  if (cfg.fused) return has_win ? dispatch_geo<true, true>(p, sa, cfg, s) : dispatch_geo<false, true>(p, sa, cfg, s);
+  return has_win ? dispatch_geo<true, false>(p, sa, cfg, s) : dispatch_geo<false, false>(p, sa, cfg, s);
+}
+
+}  // namespace
+
+bool stream_available(const hgPlan *plan, int F, bool force) {
+  if (!plan->st_ready) return false;
+  if (force) return true;
+  static const int off = env_int("HGEF_NO_STREAM", 0);
+  if (off) return false;
+  // below ~64 MB of Y the two-pass form (everything L2-resident, one warp per segment) has the lower latency
+  if ((double)plan->num_nodes * F * 4.0 < 64.0 * 1048576.0) return false;
+  return plan->max_vdeg <= 65536;   // one sub-warp walks a vertex's hyperedges
+}
+
+int ensure_xe(hgPlan *plan, int F, cudaStream_t s);
+
+int launch_stream(hgPlan *p, const dev::Args &a, cudaStream_t s) {
+  const int F = a.F;
+  if (int rc = ensure_xe(p, F, s)) return rc;
+  StreamCfg cfg{};
+  // geometry: SW lanes x VPL 128-bit vectors per row slab
+  int slabF = env_int("HGEF_ST_SLAB", 0);
+  if (slabF <= 0) slabF = F <= 512 ? F : 512;
+  if (slabF > 512) slabF = 512;
+  slabF = (slabF + 3) / 4 * 4;
+  if (slabF > F) slabF = F;
+  cfg.slabF = slabF;
+  cfg.nslab = (F + slabF - 1) / slabF;
+  cfg.sw = slabF <= 16 ? 4 : (slabF <= 32 ? 8 : (slabF <= 64 ? 16 : 32));
+  cfg.vpl = slabF <= 128 ? 1 : (slabF <= 256 ? 2 : 4);
+  const int ksub = 32 / cfg.sw;
+  // run length per row stream: ~32 KB of gathered rows per warp item by default
+  int L = env_int("HGEF_ST_L", 0);
+  if (L <= 0) {
+    L = (32 * 1024) / (slabF * 4 * ksub);
+    if (L < kL0) L = kL0;
+    if (L > 256) L = 256;
+  }
+  cfg.k0 = (L + kL0 - 1) / kL0;
+  cfg.ctas = env_int("HGEF_ST_CTAS", 0);
+  cfg.occ = env_int("HGEF_ST_OCC", 3);
+  cfg.fused = env_int("HGEF_ST_FUSED", 0) != 0;
+  cfg.lag = env_int("HGEF_ST_LAG", -1);
+  const int bpi = cfg.k0 * ksub;
+  const bool has_win = a.a_in != nullptr;
+
+  if (p->nheavy_segs > 0) {
+    zero_rows_kernel<<<(unsigned)ceil_div<int64_t>(p->nheavy_segs * 32, 256), 256, 0, s>>>(
+        p->nheavy_segs, p->heavy_segs, p->seg_edge, p->xe, F);
+    HG_CUDA_TRY(cudaGetLastError());
+    ++p->kernels_launched;
+  }
+  StreamArgs sa{};
+  sa.src[0] = p->st_srcA; sa.dst[0] = p->st_dstA; sa.run[0] = p->st_runA; sa.nrun0[0] = (int32_t)p->st_nrunA;
+  sa.src[1] = p->st_srcB; sa.dst[1] = p->st_dstB; sa.run[1] = p->st_runB; sa.nrun0[1] = (int32_t)p->st_nrunB;
+  sa.in[0] = a.X; sa.out[0] = p->xe; sa.w_in[0] = a.a_in; sa.w_o1[0] = a.s1; sa.w_o2[0] = a.s2;
+  sa.in[1] = p->xe; sa.out[1] = a.Y; sa.w_in[1] = nullptr; sa.w_o1[1] = a.a_out; sa.w_o2[1] = nullptr;
+  sa.iso = p->st_perm + p->st_nunitB; sa.niso = (int32_t)p->st_niso;
+  sa.nslab = cfg.nslab; sa.slabF = cfg.slabF; sa.F = F; sa.k0 = cfg.k0;
+  sa.y_stream = env_int("HGEF_ST_CS", 1);
+  const int32_t GA = (int32_t)ceil_div<int64_t>(p->st_nrunA, bpi), GB = (int32_t)ceil_div<int64_t>(p->st_nrunB, bpi);
+
+  if (cfg.fused) {
+    if (cfg.lag < 0) cfg.lag = 2 * kBlk;
+    hgPlan::StreamSched *sc = nullptr;
+    if (int rc = get_sched(p, bpi, cfg.lag, cfg.nslab, s, &sc)) return rc;
+    HG_CUDA_TRY(cudaMemsetAsync(sc->ctrl, 0, ((size_t)kCtrlHdr + (size_t)sc->nblk * cfg.nslab) * sizeof(int32_t), s));
+    sa.sched = sc->sched; sa.ctrl = sc->ctrl; sa.nitem = sc->GA + sc->GB; sa.nblk = sc->nblk; sa.GA = sc->GA;
+    p->st_last_ctrl = sc->ctrl;
+    ++p->kernels_launched;
+    return dispatch(p, sa, cfg, has_win, s);
+  }
+  // two launches, each stage its own ticket counter
+  HG_CUDA_TRY(cudaMemsetAsync(p->st_ctrl, 0, 2 * kCtrlHdr * sizeof(int32_t), s));
+  const int only = env_int("HGEF_ST_ONLY", 0);   // timing: 1 = stage A, 2 = stage B
+  if (only != 2) {
+    sa.stage = 0; sa.nitem = GA; sa.ctrl = p->st_ctrl;
+    ++p->kernels_launched;
+    if (int rc = dispatch(p, sa, cfg, has_win, s)) return rc;
+  }
+  if (only == 1) return HG_OK;
+  sa.stage = 1; sa.nitem = GB; sa.ctrl = p->st_ctrl + kCtrlHdr;
+  ++p->kernels_launched;
+  return dispatch(p, sa, cfg, false, s);
+}
+
+int stream_check(hgPlan *plan, cudaStream_t s) {
+  if (!plan->st_last_ctrl) return HG_OK;
+  int32_t stalled = 0;
+  HG_CUDA_TRY(cudaMemcpyAsync(&stalled, plan->st_last_ctrl + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  HG_CUDA_TRY(cudaStreamSynchronize(s));
+  if (stalled)
+    return set_error(HG_ECUDA, "stream aggregation: a stage-B item gave up waiting for its hyperedge features; "
+                               "the last result is invalid");
+  return HG_OK;
+}
+
+}  // namespace hg

@@ -121,8 +121,11 @@ enum {
   HG_FORCE_SCALAR = 4,   /* disable the 128-bit path (testing) */
   HG_TWO_PASS = 8,       /* always memset + segment kernels (the form chosen for small / long-segment graphs) */
   HG_FORCE_FUSED = 16,   /* always the single persistent scatter launch */
-  HG_FORCE_PULL = 32     /* always the gather-only two-phase form (Xe through L2/HBM, no reductions; the form
-                            chosen when Y exceeds the L2 and units are short) */
+  HG_FORCE_PULL = 32,    /* always the gather-only two-phase form with shared-memory staging (Xe through L2/HBM,
+                            no reductions; the earlier form, kept for A/B) */
+  HG_FORCE_STREAM = 64   /* always the stream form: both stages as register-only row streams, one persistent launch
+                            with the hyperedge features handed over through the L2 (the form chosen when Y exceeds
+                            the L2) */
 };
 
 /* ------------------------------------------------------------------------- *

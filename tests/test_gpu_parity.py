@@ -19,13 +19,19 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-5
 
 
-@pytest.fixture(params=["auto", "fused", "two_pass", "pull"])
+@pytest.fixture(params=["auto", "fused", "two_pass", "pull", "stream", "stream2"])
 def kernel_form(request):
     """Run a test with the library's own choice of kernel form, then with each form forced
-    (the persistent kernel is only chosen on its own when Y exceeds the L2)."""
+    (the large-graph forms are only chosen on their own when Y exceeds the L2).  "stream" is the
+    single persistent launch, "stream2" the same row streams as two launches."""
+    import os
     ops.DEFAULT_FLAGS = {"auto": 0, "fused": _native.HG_FORCE_FUSED, "two_pass": _native.HG_TWO_PASS,
-                         "pull": _native.HG_FORCE_PULL}[request.param]
+                         "pull": _native.HG_FORCE_PULL, "stream": _native.HG_FORCE_STREAM,
+                         "stream2": _native.HG_FORCE_STREAM}[request.param]
+    if request.param in ("stream", "stream2"):
+        os.environ["HGEF_ST_FUSED"] = "1" if request.param == "stream" else "0"
     yield request.param
+    os.environ.pop("HGEF_ST_FUSED", None)
     ops.DEFAULT_FLAGS = 0
 
 
@@ -146,7 +152,8 @@ def test_plan_sees_heavy_hyperedges_and_schedules_agree(cuda_device):
     want = orc.c_aggr_groups(d["group_key"], d["group_row"], d["group_start"], d["group_end"], d["H_T_colind"],
                              d["X"], s1=d["degE"], a_out=d["degV"])
     assert orc.rel_err(_np(Y1), want) < TOL and orc.rel_err(_np(Y2), want) < TOL
-    for flag in (_native.HG_FORCE_SCALAR, _native.HG_TWO_PASS, _native.HG_FORCE_FUSED, _native.HG_FORCE_PULL):
+    for flag in (_native.HG_FORCE_SCALAR, _native.HG_TWO_PASS, _native.HG_FORCE_FUSED, _native.HG_FORCE_PULL,
+                 _native.HG_FORCE_STREAM):
         Y3 = ops.aggregate(plan, X, s1=hg.degE, a_out=hg.degV, flags=flag)
         assert orc.rel_err(_np(Y3), want) < TOL
     plan.check()
@@ -271,6 +278,48 @@ def test_full_size_properties(cuda_device, kernel_form):
         0, rows, X.double()[hg.H_T_colind.long()])
     want = (xe * deg[:, None]).sum(0)
     assert ((yu.double().sum(0) - want).abs().max() / want.abs().max()).item() < 1e-6
+
+
+@pytest.mark.parametrize("shape,replicas", [("pubmed", 3), ("walmart", 1), ("dblp", 2)])
+def test_stream_form_configurations(shape, replicas, cuda_device, monkeypatch):
+    """The stream form under every scheduling knob (item length, column slabs, lag, one launch or two),
+    forward and transposed, against the two-pass kernels and (one configuration) the fp64 oracle.
+    Each fused configuration is bit-identical run to run (fixed summation order, no atomics for light
+    hyperedges) -- checked where the graph has no heavy hyperedge."""
+    data = synth.make_shape(shape, replicas=replicas, seed=3)
+    hg = HyperGraph(data, cuda_device, data.dataset)
+    N, M = hg.num_nodes, hg.num_edges
+    plan = ops.get_plan(hg.group_key, hg.group_row, hg.group_start, hg.group_end, hg.H_T_colind, N, M)
+    W = torch.rand(M, device=cuda_device) + 0.5
+    for F in (4, 20, 32, 64, 100, 128, 256, 384, 512, 640):
+        X = torch.randn(N, F, device=cuda_device)
+        ref = ops.aggregate(plan, X, s1=hg.degE, s2=W, a_out=hg.degV, flags=_native.HG_TWO_PASS)
+        ref_t = ops.aggregate(plan, X, s1=hg.degE, s2=W, a_in=hg.degV, flags=_native.HG_TWO_PASS)
+        scale, scale_t = ref.abs().max().item(), ref_t.abs().max().item()
+        combos = [dict(HGEF_ST_FUSED="1"), dict(HGEF_ST_FUSED="0"), dict(HGEF_ST_FUSED="1", HGEF_ST_L="16", HGEF_ST_LAG="0"),
+                  dict(HGEF_ST_FUSED="1", HGEF_ST_L="16", HGEF_ST_LAG="1000000"),
+                  dict(HGEF_ST_FUSED="1", HGEF_ST_L="48", HGEF_ST_SLAB="32"),
+                  dict(HGEF_ST_FUSED="1", HGEF_ST_L="256", HGEF_ST_SLAB="128", HGEF_ST_CTAS="1"),
+                  dict(HGEF_ST_OCC="4"),
+                  dict(HGEF_ST_FUSED="0", HGEF_ST_SLAB="64", HGEF_ST_L="16")]
+        for env in combos:
+            for k in ("HGEF_ST_FUSED", "HGEF_ST_L", "HGEF_ST_LAG", "HGEF_ST_SLAB", "HGEF_ST_CTAS", "HGEF_ST_OCC"):
+                monkeypatch.delenv(k, raising=False)
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            out = torch.full((N, F), float("nan"), device=cuda_device)
+            ops.aggregate(plan, X, s1=hg.degE, s2=W, a_out=hg.degV, out=out, flags=_native.HG_FORCE_STREAM)
+            assert ((out - ref).abs().max().item() / scale) < TOL, (shape, F, env)
+            out_t = ops.aggregate(plan, X, s1=hg.degE, s2=W, a_in=hg.degV, flags=_native.HG_FORCE_STREAM)
+            assert ((out_t - ref_t).abs().max().item() / scale_t) < TOL, (shape, F, env, "transposed")
+            if plan.nheavy_edges == 0:
+                again = ops.aggregate(plan, X, s1=hg.degE, s2=W, a_out=hg.degV, flags=_native.HG_FORCE_STREAM)
+                assert torch.equal(again, out), (shape, F, env, "run-to-run")
+            plan.check()
+        if F == 64:
+            want = orc.c_aggr_formula(_np(hg.H_T_csrptr), _np(hg.H_T_colind), X.cpu(), s1=_np(hg.degE).ravel() * _np(W),
+                                      a_out=_np(hg.degV))
+            assert orc.rel_err(_np(out), want) < TOL
 
 
 # ------------------------------------------------------------------ error behaviour
@@ -420,7 +469,7 @@ def test_ragged_and_degenerate_graphs(cuda_device):
             want = orc.c_aggr_formula(ptr, ind, X, s1=_np(hg.degE), a_out=_np(hg.degV))
             out = torch.full((N, F), float("nan"), device=cuda_device)
             plan = ops.get_plan(hg.group_key, hg.group_row, hg.group_start, hg.group_end, hg.H_T_colind, N, hg.num_edges)
-            for flags in (0, _native.HG_TWO_PASS, _native.HG_FORCE_FUSED, _native.HG_FORCE_PULL):
+            for flags in (0, _native.HG_TWO_PASS, _native.HG_FORCE_FUSED, _native.HG_FORCE_PULL, _native.HG_FORCE_STREAM):
                 ops.aggregate(plan, X.to(cuda_device), s1=hg.degE, a_out=hg.degV, out=out, flags=flags)
                 assert orc.rel_err(_np(out), want) < TOL or np.abs(want).max() == 0, (len(members), N, ngs, F, flags)
             plan.check()

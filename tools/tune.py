@@ -14,7 +14,9 @@ ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--two-pass", action="store_true")
 ap.add_argument("--force-fused", action="store_true")
 ap.add_argument("--force-pull", action="store_true")
+ap.add_argument("--force-stream", action="store_true")
 ap.add_argument("--tag", default="")
+ap.add_argument("--sweep", default="", help="semicolon-separated env configs K=V,K=V applied in-process (stream form knobs are read per call)")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 data = synth.make_shape(args.shape, replicas=args.replicas, seed=0, device=dev)
@@ -22,19 +24,26 @@ hg = hgef.HyperGraph(data, dev, data.dataset)
 N, M, Z = hg.num_nodes, hg.num_edges, hg.H_T_colind.numel()
 plan = ops.get_plan(hg.group_key, hg.group_row, hg.group_start, hg.group_end, hg.H_T_colind, N, M)
 W = torch.ones(M, device=dev)
-flags = _native.HG_TWO_PASS if args.two_pass else (_native.HG_FORCE_FUSED if args.force_fused else (_native.HG_FORCE_PULL if args.force_pull else 0))
-out = []
-for F in [int(f) for f in args.features.split(",")]:
-    X = torch.randn(N, F, device=dev); Y = torch.empty(N, F, device=dev)
-    for _ in range(3):
-        ops.aggregate(plan, X, s1=hg.degE, s2=W, a_out=hg.degV, out=Y, flags=flags)
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(args.iters):
-        ops.aggregate(plan, X, s1=hg.degE, s2=W, a_out=hg.degV, out=Y, flags=flags)
-    b.record(); torch.cuda.synchronize(); plan.check()
-    us = a.elapsed_time(b) / args.iters * 1e3
-    balg = 8 * F * N + 4 * Z + 12 * M + 4 * N + 4
-    out.append(f"F={F}: {us:8.1f} us {balg / us / 1e3:7.1f} GB/s ({balg / us / 1e3 / 6536 * 100:4.1f}%)")
-    del X, Y
-print(f"[{args.tag} {args.shape}x{args.replicas} N={N} Z={Z} heavy={plan.nheavy_edges}] " + " | ".join(out), flush=True)
+flags = _native.HG_TWO_PASS if args.two_pass else (_native.HG_FORCE_FUSED if args.force_fused else (_native.HG_FORCE_PULL if args.force_pull else (_native.HG_FORCE_STREAM if args.force_stream else 0)))
+KNOBS = ("HGEF_ST_FUSED", "HGEF_ST_L", "HGEF_ST_LAG", "HGEF_ST_SLAB", "HGEF_ST_CTAS", "HGEF_ST_ONLY", "HGEF_ST_OCC", "HGEF_ST_CS")
+for cfg in (args.sweep.split(";") if args.sweep else [""]):
+    for k in (KNOBS if args.sweep else ()):
+        os.environ.pop(k, None)
+    for kv in filter(None, cfg.split(",")):
+        k, v = kv.split("=")
+        os.environ[k if k.startswith("HGEF_") else "HGEF_ST_" + k] = v
+    out = []
+    for F in [int(f) for f in args.features.split(",")]:
+        X = torch.randn(N, F, device=dev); Y = torch.empty(N, F, device=dev)
+        for _ in range(3):
+            ops.aggregate(plan, X, s1=hg.degE, s2=W, a_out=hg.degV, out=Y, flags=flags)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(args.iters):
+            ops.aggregate(plan, X, s1=hg.degE, s2=W, a_out=hg.degV, out=Y, flags=flags)
+        b.record(); torch.cuda.synchronize(); plan.check()
+        us = a.elapsed_time(b) / args.iters * 1e3
+        balg = 8 * F * N + 4 * Z + 12 * M + 4 * N + 4
+        out.append(f"F={F}: {us:8.1f} us {balg / us / 1e3:7.1f} GB/s ({balg / us / 1e3 / 6536 * 100:4.1f}%)")
+        del X, Y
+    print(f"[{args.tag} {cfg} {args.shape}x{args.replicas} N={N} Z={Z} heavy={plan.nheavy_edges}] " + " | ".join(out), flush=True)

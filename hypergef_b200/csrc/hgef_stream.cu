@@ -38,7 +38,8 @@ namespace hg {
 namespace {
 using namespace dev;
 
-constexpr uint32_t kEnd = 0x80000000u, kRowMask = 0x7fffffffu;
+// dst word: bit31 = last member of its unit, bit30 = heavy (reduce into the row), low 30 bits = output row
+constexpr uint32_t kEnd = 0x80000000u, kHeavy = 0x40000000u, kIdMask = 0x3fffffffu, kRowMask = kIdMask;
 constexpr int kL0 = 16;      // positions per base run
 constexpr int kBlk = 8;      // A items per completion counter
 constexpr int kVec = 8;      // 128-bit row loads in flight per lane
@@ -93,13 +94,22 @@ template <int SW, int VPL>
 struct SGeo {
   static constexpr int kSub = 32 / SW;                          // row streams per warp
   static constexpr int kU = (kVec / VPL) < SW ? (kVec / VPL) : SW;   // rows in flight per stream
+  static constexpr int kHB = kU >= 2 ? kU / 2 : 1;              // rows per half-batch (two register sets alternate)
+  static constexpr int kNH = SW / kHB;                          // half-batches per chunk of SW positions (even)
   static constexpr int kStride = SW * 4;                        // floats between a lane's vectors
 };
 
-template <int SW, int VPL, bool HAS_WIN, bool FUSED, int MINB>
+// STAGE 0 / 1: the launch runs one stage (its arrays are addressed straight from the constant bank);
+// STAGE -1: fused launch, the stage comes with the ticket.
+// PIPE: rows are loaded in half-batches into two alternating register sets (half h + 1 is issued before half
+// h is consumed); otherwise whole batches are loaded and then consumed (better for the widest rows, where
+// a half-batch is a single 2 KB row).
+template <int SW, int VPL, bool HAS_WIN, int STAGE, int MINB, bool PIPE>
 __global__ void __launch_bounds__(kThreads, MINB) stream_kernel(const StreamArgs sa) {
   using G = SGeo<SW, VPL>;
-  constexpr int U = G::kU;
+  constexpr bool FUSED = STAGE < 0;
+  constexpr int HB = PIPE ? G::kHB : G::kU, NH = SW / HB;
+  static_assert(!PIPE || (NH >= 2 && NH % 2 == 0), "a chunk is a whole number of half-batch pairs");
   const int lane = threadIdx.x & 31;
   const int sub = lane / SW, sl = lane % SW;
   const int col = sl * 4;
@@ -107,6 +117,9 @@ __global__ void __launch_bounds__(kThreads, MINB) stream_kernel(const StreamArgs
   const uint32_t row_bytes = (uint32_t)F * 4u;
   const int total = sa.nitem * sa.nslab;
   int blk_wm = 0, wm_slab = 0;
+  uint32_t pat = 0;   // bit (stream * SW) for every row stream of the warp
+#pragma unroll
+  for (int q = 0; q < G::kSub; ++q) pat |= 1u << (q * SW);
 
   for (;;) {
     int t = 0;
@@ -117,25 +130,29 @@ __global__ void __launch_bounds__(kThreads, MINB) stream_kernel(const StreamArgs
     const int k = t - slab * sa.nitem;
     const int col0 = slab * sa.slabF;
     const int Fs = min(sa.slabF, F - col0);
-    int stage = sa.stage, gid = k, need = 0;
+    int stage = FUSED ? 0 : STAGE, gid = k, need = 0;
     if (FUSED) {
       const int2 s = __ldg(sa.sched + k);
       stage = s.x & 1;
       gid = s.x >> 1;
       need = s.y;
     }
+    const float *in = sa.in[stage] + col0;
+    float *out = sa.out[stage] + col0;
     // column mask of this lane's vectors; a masked vector LOADS column 0 of the slab instead (no branch
     // around the load) and is never stored
     bool ok[VPL];
     int off[VPL];
+    const char *in_v[VPL];
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
       ok[v] = col + v * G::kStride < Fs;
       off[v] = ok[v] ? col + v * G::kStride : 0;
+      in_v[v] = reinterpret_cast<const char *>(in + off[v]);
     }
 
     // this ticket's share of the vertices that no hyperedge touches (only the B side has any)
-    if (sa.niso > 0 && (FUSED || stage == 1)) {
+    if (sa.niso > 0 && (FUSED || STAGE == 1)) {
       const int i0 = (int)((int64_t)sa.niso * k / sa.nitem), i1 = (int)((int64_t)sa.niso * (k + 1) / sa.nitem);
       for (int i = i0 + sub; i < i1; i += G::kSub) {
         float *yp = sa.out[1] + (int64_t)__ldg(sa.iso + i) * F + col0;
@@ -147,8 +164,6 @@ __global__ void __launch_bounds__(kThreads, MINB) stream_kernel(const StreamArgs
 
     const int32_t *__restrict__ src = sa.src[stage];
     const int32_t *__restrict__ dst = sa.dst[stage];
-    const float *in = sa.in[stage] + col0;
-    float *out = sa.out[stage] + col0;
     const float *__restrict__ w_in = sa.w_in[stage];
     const float *__restrict__ w_o1 = sa.w_o1[stage];
     const float *__restrict__ w_o2 = sa.w_o2[stage];
@@ -183,7 +198,9 @@ __global__ void __launch_bounds__(kThreads, MINB) stream_kernel(const StreamArgs
       }
     }
 
-    // ---- stream the run: chunks of SW positions, their src/dst words one per lane ----
+    // ---- stream the run.  Chunks of SW positions: their src / dst words one per lane, handed out by
+    // shuffles.  Rows are loaded in half-batches of HB rows into two alternating register sets: half
+    // h + 1 is issued before half h is consumed, so a stream always has HB..2HB row loads in flight.
     float4 acc[VPL];
 #pragma unroll
     for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -193,48 +210,43 @@ __global__ void __launch_bounds__(kThreads, MINB) stream_kernel(const StreamArgs
       c_src = (uint32_t)__ldg(src + cb + sl);
       c_dst = (uint32_t)__ldg(dst + cb + sl);
     }
+    float4 x0[HB][VPL], x1[HB][VPL];
+    // (positions past the end of the run carry src word 0: row 0 is loaded and never used for output --
+    //  a run ends with a unit end, which resets `acc`, and `acc` restarts from zero with every item)
+    auto load_half = [&](float4(&x)[HB][VPL], uint32_t words, int j0) {
+#pragma unroll
+      for (int u = 0; u < HB; ++u) {
+        const uint32_t id = __shfl_sync(kFull, words, j0 + u, SW);
+        const uint64_t rb = (uint64_t)id * row_bytes;   // one IMAD.WIDE.U32 per vector below
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) x[u][v] = ld_row16<FUSED>(reinterpret_cast<const float *>(in_v[v] + rb));
+      }
+    };
+    if (PIPE) load_half(x0, c_src, 0);
     while (__any_sync(kFull, cb < pe)) {
       float c_w = 1.0f, c_sc = 1.0f;
       if (cb + sl < pe) {
-        if (HAS_WIN && w_in) c_w = __ldg(w_in + (c_src & kRowMask));
-        if (c_src & kEnd) {
+        if (HAS_WIN && w_in) c_w = __ldg(w_in + c_src);
+        if (c_dst & kEnd) {
           const uint32_t orow = c_dst & kRowMask;
           if (w_o1) c_sc = __ldg(w_o1 + orow);
           if (w_o2) c_sc *= __ldg(w_o2 + orow);
         }
       }
+      // unit-end flags of the chunk: bit (stream * SW + position); a step whose position ends no unit in
+      // any stream of the warp skips the output bookkeeping with one uniform test
+      const uint32_t endm = __ballot_sync(kFull, (c_dst & kEnd) != 0);
       uint32_t n_src = 0, n_dst = 0;   // next chunk's words: in flight while this chunk streams
       if (cb + SW + sl < pe) {
         n_src = (uint32_t)__ldg(src + cb + SW + sl);
         n_dst = (uint32_t)__ldg(dst + cb + SW + sl);
       }
-#pragma unroll 1
-      for (int b = 0; b < SW; b += U) {
-        if (!__any_sync(kFull, cb + b < pe)) break;
-        float4 x[U][VPL];
-        uint32_t id[U];
+      auto consume_half = [&](const float4(&x)[HB][VPL], int j0) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          // (positions past the end of the run carry src word 0: row 0 is loaded and ignored)
-          id[u] = __shfl_sync(kFull, c_src, b + u, SW);
-          const uint64_t rb = (uint64_t)(id[u] & kRowMask) * row_bytes;   // one IMAD.WIDE.U32
-#pragma unroll
-          for (int v = 0; v < VPL; ++v)
-            x[u][v] = ld_row16<FUSED>(reinterpret_cast<const float *>(reinterpret_cast<const char *>(in + off[v]) + rb));
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          // Positions past the end of the run gathered row 0 and carry no END flag: what they add to
-          // `acc` is never stored (a run ends with an END, and `acc` restarts from zero per item).
+        for (int u = 0; u < HB; ++u) {
+          const int j = j0 + u;
           float w = 1.0f;
-          if (HAS_WIN) w = __shfl_sync(kFull, c_w, b + u, SW);
-          const bool end = (id[u] & kEnd) != 0;
-          uint32_t d = 0;
-          float sc = 1.0f;
-          if (SW < 32 || end) {   // (a whole-warp stream branches uniformly; sub-warps shuffle unconditionally)
-            d = __shfl_sync(kFull, c_dst, b + u, SW);
-            sc = __shfl_sync(kFull, c_sc, b + u, SW);
-          }
+          if (HAS_WIN) w = __shfl_sync(kFull, c_w, j, SW);
 #pragma unroll
           for (int v = 0; v < VPL; ++v) {
             if (HAS_WIN) {
@@ -249,20 +261,42 @@ __global__ void __launch_bounds__(kThreads, MINB) stream_kernel(const StreamArgs
               acc[v].w += x[u][v].w;
             }
           }
-          if (end) {   // unit complete: one output row
-            char *op = reinterpret_cast<char *>(out) + (uint64_t)(d & kRowMask) * row_bytes;
+          if (endm & (pat << j)) {   // warp-uniform: some stream finishes a unit at this position
+            const uint32_t d = __shfl_sync(kFull, c_dst, j, SW);
+            const float sc = __shfl_sync(kFull, c_sc, j, SW);
+            if (d & kEnd) {          // this stream does: one output row
+              char *op = reinterpret_cast<char *>(out) + (uint64_t)(d & kIdMask) * row_bytes;
 #pragma unroll
-            for (int v = 0; v < VPL; ++v) {
-              if (ok[v]) {
-                const float4 r = make_float4(acc[v].x * sc, acc[v].y * sc, acc[v].z * sc, acc[v].w * sc);
-                float *o = reinterpret_cast<float *>(op) + off[v];
-                if (d & kEnd) red_add_v4(o, r);
-                else if (stage == 1 && sa.y_stream) st_row16_stream(o, r);
-                else st_row16(o, r);
+              for (int v = 0; v < VPL; ++v) {
+                if (ok[v]) {
+                  const float4 r = make_float4(acc[v].x * sc, acc[v].y * sc, acc[v].z * sc, acc[v].w * sc);
+                  float *o = reinterpret_cast<float *>(op) + off[v];
+                  if (d & kHeavy) red_add_v4(o, r);
+                  else if (stage == 1 && sa.y_stream) st_row16_stream(o, r);
+                  else st_row16(o, r);
+                }
+                acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
               }
-              acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
           }
+        }
+      };
+      if constexpr (PIPE) {
+#pragma unroll 1
+        for (int h = 0; h < NH; h += 2) {
+          if (h > 0 && !__any_sync(kFull, cb + h * HB < pe)) break;
+          load_half(x1, c_src, (h + 1) * HB);
+          consume_half(x0, h * HB);
+          if (h + 2 < NH) load_half(x0, c_src, (h + 2) * HB);
+          else load_half(x0, n_src, 0);                      // first half of the next chunk
+          consume_half(x1, (h + 1) * HB);
+        }
+      } else {
+#pragma unroll 1
+        for (int h = 0; h < NH; ++h) {
+          if (h > 0 && !__any_sync(kFull, cb + h * HB < pe)) break;
+          load_half(x0, c_src, h * HB);
+          consume_half(x0, h * HB);
         }
       }
       cb += SW;
@@ -298,13 +332,11 @@ __global__ void prog_fill_kernel(int64_t nunit, const int32_t *__restrict__ ptr_
   const int32_t u = unit_of ? unit_of[i] : (int32_t)i;
   const int32_t a = ptr_in[u], n = ptr_in[u + 1] - a, o = ptr_out[i];
   uint32_t d = (uint32_t)(out_row ? out_row[u] : u);
-  if (heavy_slot && heavy_slot[u] >= 0) d |= kEnd;
+  if (heavy_slot && heavy_slot[u] >= 0) d |= kHeavy;
   const int32_t nd = unit_need ? unit_need[i] : 0;
   for (int32_t j = lane; j < n; j += 32) {
-    uint32_t s = (uint32_t)ind[a + j];
-    if (j == n - 1) s |= kEnd;
-    src[o + j] = (int32_t)s;
-    dst[o + j] = (int32_t)d;
+    src[o + j] = ind[a + j];
+    dst[o + j] = (int32_t)(j == n - 1 ? d | kEnd : d);
     if (need) need[o + j] = nd;
   }
 }
@@ -440,6 +472,7 @@ void stream_free(hgPlan *p) {
 int build_stream(hgPlan *p, cudaStream_t s) {
   const int64_t N = p->num_nodes, M = p->num_edges, Z = p->nnz, S = p->nseg;
   if (!p->canonical || p->h_ptr == nullptr || Z == 0) return HG_OK;
+  if (N >= (int64_t(1) << 30) || M >= (int64_t(1) << 30)) return HG_OK;   // row ids share a word with two flags
   {   // the segments must tile [0, Z) exactly (the balancer's do)
     int32_t k0 = -1, kS = -1;
     HG_CUDA_TRY(cudaMemcpyAsync(&k0, p->key, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
@@ -552,12 +585,13 @@ int get_sched(hgPlan *p, int bpi, int lag, int nslab, cudaStream_t s, hgPlan::St
 
 struct StreamCfg {
   int sw, vpl, slabF, nslab, k0, ctas, lag, occ;
-  bool fused;
+  bool fused, pipe;
 };
 
-template <int SW, int VPL, bool HAS_WIN, bool FUSED>
+template <int SW, int VPL, bool HAS_WIN, int STAGE>
 int launch_one(hgPlan *p, StreamArgs &sa, const StreamCfg &cfg, cudaStream_t s) {
-  auto kern = cfg.occ == 4 ? stream_kernel<SW, VPL, HAS_WIN, FUSED, 4> : stream_kernel<SW, VPL, HAS_WIN, FUSED, 3>;
+  auto kern = cfg.pipe ? (cfg.occ == 4 ? stream_kernel<SW, VPL, HAS_WIN, STAGE, 4, true> : stream_kernel<SW, VPL, HAS_WIN, STAGE, 3, true>)
+                       : stream_kernel<SW, VPL, HAS_WIN, STAGE, 3, false>;
   int per_sm = 0;
   HG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0));
   if (per_sm < 1) per_sm = 1;
@@ -571,18 +605,19 @@ int launch_one(hgPlan *p, StreamArgs &sa, const StreamCfg &cfg, cudaStream_t s) 
   return HG_OK;
 }
 
-template <bool HAS_WIN, bool FUSED>
-int dispatch_geo(hgPlan *p, StreamArgs &sa, const StreamCfg &cfg, cudaStream_t s) {
-#define HG_CASE(SW_, VPL_) \
-  if (cfg.sw == SW_ && cfg.vpl == VPL_) return launch_one<SW_, VPL_, HAS_WIN, FUSED>(p, sa, cfg, s)
-  HG_CASE(4, 1); HG_CASE(8, 1); HG_CASE(16, 1); HG_CASE(32, 1); HG_CASE(32, 2); HG_CASE(32, 4);
+// stage: 0 / 1 = one stage per launch, -1 = fused
+int dispatch(hgPlan *p, StreamArgs &sa, const StreamCfg &cfg, int stage, bool has_win, cudaStream_t s) {
+#define HG_CASE(SW_, VPL_)                                                                             \
+  if (cfg.sw == SW_ && cfg.vpl == VPL_) {                                                              \
+    if (stage < 0)                                                                                     \
+      return has_win ? launch_one<SW_, VPL_, true, -1>(p, sa, cfg, s) : launch_one<SW_, VPL_, false, -1>(p, sa, cfg, s); \
+    if (stage == 1) return launch_one<SW_, VPL_, false, 1>(p, sa, cfg, s);                             \
+    return has_win ? launch_one<SW_, VPL_, true, 0>(p, sa, cfg, s) : launch_one<SW_, VPL_, false, 0>(p, sa, cfg, s);    \
+  }
+  HG_CASE(4, 1) HG_CASE(4, 2) HG_CASE(4, 4) HG_CASE(8, 1) HG_CASE(8, 2) HG_CASE(8, 4)
+  HG_CASE(16, 1) HG_CASE(16, 2) HG_CASE(16, 4) HG_CASE(32, 1) HG_CASE(32, 2) HG_CASE(32, 4)
 #undef HG_CASE
   return set_error(HG_EINVAL, "stream: no kernel for sub-warp %d x %d vectors", cfg.sw, cfg.vpl);
-}
-
-int dispatch(hgPlan *p, StreamArgs &sa, const StreamCfg &cfg, bool has_win, cudaStream_t s) {
-  if (cfg.fused) return has_win ? dispatch_geo<true, true>(p, sa, cfg, s) : dispatch_geo<false, true>(p, sa, cfg, s);
-  return has_win ? dispatch_geo<true, false>(p, sa, cfg, s) : dispatch_geo<false, false>(p, sa, cfg, s);
 }
 
 }  // namespace
@@ -612,7 +647,12 @@ int launch_stream(hgPlan *p, const dev::Args &a, cudaStream_t s) {
   cfg.slabF = slabF;
   cfg.nslab = (F + slabF - 1) / slabF;
   cfg.sw = slabF <= 16 ? 4 : (slabF <= 32 ? 8 : (slabF <= 64 ? 16 : 32));
-  cfg.vpl = slabF <= 128 ? 1 : (slabF <= 256 ? 2 : 4);
+  {   // HGEF_ST_SW: lanes per row (the lane then holds 1, 2 or 4 vectors of the row)
+    const int sw_env = env_int("HGEF_ST_SW", 0);
+    if (sw_env == 4 || sw_env == 8 || sw_env == 16 || sw_env == 32) cfg.sw = sw_env;
+    while (cfg.sw < 32 && slabF > cfg.sw * 16) cfg.sw *= 2;
+  }
+  cfg.vpl = slabF <= cfg.sw * 4 ? 1 : (slabF <= cfg.sw * 8 ? 2 : 4);
   const int ksub = 32 / cfg.sw;
   // run length per row stream: ~32 KB of gathered rows per warp item by default
   int L = env_int("HGEF_ST_L", 0);
@@ -624,6 +664,7 @@ int launch_stream(hgPlan *p, const dev::Args &a, cudaStream_t s) {
   cfg.k0 = (L + kL0 - 1) / kL0;
   cfg.ctas = env_int("HGEF_ST_CTAS", 0);
   cfg.occ = env_int("HGEF_ST_OCC", 3);
+  cfg.pipe = env_int("HGEF_ST_PIPE", cfg.vpl < 4 ? 1 : 0) != 0;
   cfg.fused = env_int("HGEF_ST_FUSED", 0) != 0;
   cfg.lag = env_int("HGEF_ST_LAG", -1);
   const int bpi = cfg.k0 * ksub;
@@ -653,7 +694,7 @@ int launch_stream(hgPlan *p, const dev::Args &a, cudaStream_t s) {
     sa.sched = sc->sched; sa.ctrl = sc->ctrl; sa.nitem = sc->GA + sc->GB; sa.nblk = sc->nblk; sa.GA = sc->GA;
     p->st_last_ctrl = sc->ctrl;
     ++p->kernels_launched;
-    return dispatch(p, sa, cfg, has_win, s);
+    return dispatch(p, sa, cfg, -1, has_win, s);
   }
   // two launches, each stage its own ticket counter
   HG_CUDA_TRY(cudaMemsetAsync(p->st_ctrl, 0, 2 * kCtrlHdr * sizeof(int32_t), s));
@@ -661,12 +702,12 @@ int launch_stream(hgPlan *p, const dev::Args &a, cudaStream_t s) {
   if (only != 2) {
     sa.stage = 0; sa.nitem = GA; sa.ctrl = p->st_ctrl;
     ++p->kernels_launched;
-    if (int rc = dispatch(p, sa, cfg, has_win, s)) return rc;
+    if (int rc = dispatch(p, sa, cfg, 0, has_win, s)) return rc;
   }
   if (only == 1) return HG_OK;
   sa.stage = 1; sa.nitem = GB; sa.ctrl = p->st_ctrl + kCtrlHdr;
   ++p->kernels_launched;
-  return dispatch(p, sa, cfg, false, s);
+  return dispatch(p, sa, cfg, 1, false, s);
 }
 
 int stream_check(hgPlan *plan, cudaStream_t s) {

@@ -300,10 +300,11 @@ def test_stream_form_configurations(shape, replicas, cuda_device, monkeypatch):
                   dict(HGEF_ST_FUSED="1", HGEF_ST_L="16", HGEF_ST_LAG="1000000"),
                   dict(HGEF_ST_FUSED="1", HGEF_ST_L="48", HGEF_ST_SLAB="32"),
                   dict(HGEF_ST_FUSED="1", HGEF_ST_L="256", HGEF_ST_SLAB="128", HGEF_ST_CTAS="1"),
-                  dict(HGEF_ST_OCC="4"),
+                  dict(HGEF_ST_OCC="4"), dict(HGEF_ST_PIPE="0", HGEF_ST_L="32"), dict(HGEF_ST_PIPE="1", HGEF_ST_FUSED="1"),
+                  dict(HGEF_ST_SW="16"), dict(HGEF_ST_SW="8", HGEF_ST_OCC="4"), dict(HGEF_ST_SW="4", HGEF_ST_FUSED="1"),
                   dict(HGEF_ST_FUSED="0", HGEF_ST_SLAB="64", HGEF_ST_L="16")]
         for env in combos:
-            for k in ("HGEF_ST_FUSED", "HGEF_ST_L", "HGEF_ST_LAG", "HGEF_ST_SLAB", "HGEF_ST_CTAS", "HGEF_ST_OCC"):
+            for k in ("HGEF_ST_FUSED", "HGEF_ST_L", "HGEF_ST_LAG", "HGEF_ST_SLAB", "HGEF_ST_CTAS", "HGEF_ST_OCC", "HGEF_ST_SW", "HGEF_ST_PIPE"):
                 monkeypatch.delenv(k, raising=False)
             for k, v in env.items():
                 monkeypatch.setenv(k, v)

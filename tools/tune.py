@@ -25,7 +25,7 @@ N, M, Z = hg.num_nodes, hg.num_edges, hg.H_T_colind.numel()
 plan = ops.get_plan(hg.group_key, hg.group_row, hg.group_start, hg.group_end, hg.H_T_colind, N, M)
 W = torch.ones(M, device=dev)
 flags = _native.HG_TWO_PASS if args.two_pass else (_native.HG_FORCE_FUSED if args.force_fused else (_native.HG_FORCE_PULL if args.force_pull else (_native.HG_FORCE_STREAM if args.force_stream else 0)))
-KNOBS = ("HGEF_ST_FUSED", "HGEF_ST_L", "HGEF_ST_LAG", "HGEF_ST_SLAB", "HGEF_ST_CTAS", "HGEF_ST_ONLY", "HGEF_ST_OCC", "HGEF_ST_CS")
+KNOBS = ("HGEF_ST_FUSED", "HGEF_ST_L", "HGEF_ST_LAG", "HGEF_ST_SLAB", "HGEF_ST_CTAS", "HGEF_ST_ONLY", "HGEF_ST_OCC", "HGEF_ST_CS", "HGEF_ST_SW", "HGEF_ST_PIPE")
 for cfg in (args.sweep.split(";") if args.sweep else [""]):
     for k in (KNOBS if args.sweep else ()):
         os.environ.pop(k, None)

@@ -48,6 +48,7 @@ SIGNATURES = {
     "hg_aggr_forward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp],
     "hg_aggr_groups": [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32,
                        _int, _vp],
+    "hg_copy_columns": [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _int, _vp],
     "hg_edge_reduce": [_i64, _vp, _vp, _vp, _vp, _vp, _i32, _int, _vp],
     "hg_edge_scatter": [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _int, _vp],
     "hg_aggr_mean": [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _int, _vp],

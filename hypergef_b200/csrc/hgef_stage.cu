@@ -226,4 +226,22 @@ int hg_edge_scatter(int64_t nrow, const int32_t *d_indptr, const int32_t *d_indi
   return HG_OK;
 }
 
+int hg_copy_columns(void *dst, const void *src, int64_t nrow, int64_t ncol, int64_t ld_host, int64_t col0,
+                    int32_t to_device, int device, void *stream) {
+  HG_REQUIRE(dst != nullptr && src != nullptr, "copy_columns: NULL buffer");
+  HG_REQUIRE(nrow >= 0 && ncol >= 1 && col0 >= 0 && col0 + ncol <= ld_host, "copy_columns: columns [%lld, %lld) outside a row of %lld",
+             (long long)col0, (long long)(col0 + ncol), (long long)ld_host);
+  if (nrow == 0) return HG_OK;
+  DeviceGuard guard(device);
+  HG_REQUIRE(guard.ok(), "copy_columns: cannot select device %d", device);
+  const size_t w = (size_t)ncol * sizeof(float), hp = (size_t)ld_host * sizeof(float);
+  if (to_device)
+    HG_CUDA_TRY(cudaMemcpy2DAsync(dst, w, static_cast<const char *>(src) + (size_t)col0 * sizeof(float), hp, w, (size_t)nrow,
+                                  cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  else
+    HG_CUDA_TRY(cudaMemcpy2DAsync(static_cast<char *>(dst) + (size_t)col0 * sizeof(float), hp, src, w, w, (size_t)nrow,
+                                  cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return HG_OK;
+}
+
 }  // extern "C"

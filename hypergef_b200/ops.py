@@ -25,6 +25,8 @@ import ctypes as C
 import threading
 from collections import OrderedDict
 
+import os
+
 import torch
 
 from . import _native
@@ -209,18 +211,38 @@ def aggregate(plan: Plan, X, s1=None, s2=None, a_out=None, a_in=None, out=None, 
 class HostPipeline:
     """Aggregation for HOST feature matrices (numpy / CPU torch callers), copies overlapped.
 
-    Three streams: host->device copies, the aggregation launches, device->host copies.  Calls
-    submitted back to back overlap -- the upload of call k+1 and the download of call k-1 run
-    while call k computes (PCIe is full duplex) -- and all launches share ONE compute stream, so
-    the plan's per-call scratch is never used by two launches at once.  ``wait()`` blocks until
-    every submitted result is in its host buffer.  Pinned host buffers make the copies real DMA.
+    Three streams: host->device copies, the aggregation launches, device->host copies.  A matrix is
+    staged in COLUMN SLABS (the aggregation never mixes feature columns): every slab is its own
+    upload -> launch -> download through a small ring of preallocated device buffers, so the upload of
+    slab k+1 and the download of slab k-1 run while slab k computes (PCIe is full duplex) -- inside one
+    wide matrix as well as across calls -- and no allocation happens on the hot path.  All launches
+    share ONE compute stream, so the plan's per-call scratch is never used by two launches at once.
+    ``wait()`` blocks until every submitted result is in its host buffer.  Pinned host buffers make
+    the copies real DMA.
     """
 
-    def __init__(self, plan: Plan):
+    def __init__(self, plan: Plan, col_slab: int = 128, depth: int = 4):
         self.plan = plan
+        # columns per staged slab (0 = whole matrices, device buffers from the caching allocator);
+        # HGEF_COL_SLAB overrides the default for experiments
+        self.col_slab = int(os.environ.get("HGEF_COL_SLAB", col_slab))
+        self.depth = max(2, int(depth))
         with torch.cuda.device(plan.device_index):
             self.h2d, self.compute, self.d2h = (torch.cuda.Stream() for _ in range(3))
+        self._slots, self._next = [], 0
         self._keep = []
+
+    def _slot(self, width):
+        """Next staging slot (device X / Y buffers of ``num_nodes x col_slab`` floats + a 'free again' event)."""
+        if not self._slots:
+            n = self.plan.num_nodes * self.col_slab
+            for _ in range(self.depth):
+                self._slots.append({"X": torch.empty(n, dtype=torch.float32, device=self.plan.device),
+                                    "Y": torch.empty(n, dtype=torch.float32, device=self.plan.device), "free": None})
+        slot = self._slots[self._next]
+        self._next = (self._next + 1) % self.depth
+        n = self.plan.num_nodes * width
+        return slot, slot["X"][:n].view(self.plan.num_nodes, width), slot["Y"][:n].view(self.plan.num_nodes, width)
 
     def submit(self, X_host, out_host=None, s1=None, s2=None, a_out=None, a_in=None):
         plan = self.plan
@@ -234,21 +256,48 @@ class HostPipeline:
         if out_host.shape != X_host.shape or out_host.dtype != torch.float32 or out_host.is_cuda \
                 or not out_host.is_contiguous():
             raise ValueError("out_host must be a contiguous float32 CPU tensor of X_host's shape")
-        with torch.cuda.device(plan.device_index):
-            with torch.cuda.stream(self.h2d):
-                Xd = X_host.to(plan.device, non_blocking=True)
-                up = torch.cuda.Event()
-                up.record()
-            with torch.cuda.stream(self.compute):
-                self.compute.wait_event(up)
-                Yd = aggregate(plan, Xd, s1=s1, s2=s2, a_out=a_out, a_in=a_in)
-                Xd.record_stream(self.compute)
-                done = torch.cuda.Event()
-                done.record()
-            with torch.cuda.stream(self.d2h):
-                self.d2h.wait_event(done)
-                out_host.copy_(Yd, non_blocking=True)
-                Yd.record_stream(self.d2h)
+        N, F = X_host.shape
+        if N != plan.num_nodes:
+            raise ValueError(f"X_host has {N} rows, the graph has {plan.num_nodes} vertices")
+        dev = plan.device_index
+        with torch.cuda.device(dev):
+            if self.col_slab <= 0:          # whole matrix, buffers from the caching allocator
+                with torch.cuda.stream(self.h2d):
+                    Xd = X_host.to(plan.device, non_blocking=True)
+                    up = torch.cuda.Event()
+                    up.record()
+                with torch.cuda.stream(self.compute):
+                    self.compute.wait_event(up)
+                    Yd = aggregate(plan, Xd, s1=s1, s2=s2, a_out=a_out, a_in=a_in)
+                    Xd.record_stream(self.compute)
+                    done = torch.cuda.Event()
+                    done.record()
+                with torch.cuda.stream(self.d2h):
+                    self.d2h.wait_event(done)
+                    out_host.copy_(Yd, non_blocking=True)
+                    Yd.record_stream(self.d2h)
+            else:
+                for c0 in range(0, F, self.col_slab):
+                    w = min(self.col_slab, F - c0)
+                    slot, Xd, Yd = self._slot(w)
+                    with torch.cuda.stream(self.h2d):
+                        if slot["free"] is not None:
+                            self.h2d.wait_event(slot["free"])      # its previous download has finished
+                        _native.call("hg_copy_columns", Xd.data_ptr(), X_host.data_ptr(), N, w, F, c0, 1, dev,
+                                     self.h2d.cuda_stream)
+                        up = torch.cuda.Event()
+                        up.record()
+                    with torch.cuda.stream(self.compute):
+                        self.compute.wait_event(up)
+                        aggregate(plan, Xd, s1=s1, s2=s2, a_out=a_out, a_in=a_in, out=Yd)
+                        done = torch.cuda.Event()
+                        done.record()
+                    with torch.cuda.stream(self.d2h):
+                        self.d2h.wait_event(done)
+                        _native.call("hg_copy_columns", out_host.data_ptr(), Yd.data_ptr(), N, w, F, c0, 0, dev,
+                                     self.d2h.cuda_stream)
+                        slot["free"] = torch.cuda.Event()
+                        slot["free"].record()
         self._keep.append((X_host, out_host))
         return out_host
 
@@ -260,7 +309,9 @@ class HostPipeline:
 def aggregate_host(plan: Plan, X_host, out_host=None, s1=None, s2=None, a_out=None, a_in=None):
     """One blocking host-buffer aggregation: ``X_host`` [N,F] fp32 -> device -> ``hg_aggr_forward``
     -> ``out_host``.  For several matrices use :class:`HostPipeline` so the copies overlap."""
-    pipe = HostPipeline(plan)
+    pipe = getattr(plan, "_host_pipe", None)
+    if pipe is None:
+        pipe = plan._host_pipe = HostPipeline(plan, depth=2)
     out = pipe.submit(X_host, out_host, s1=s1, s2=s2, a_out=a_out, a_in=a_in)
     pipe.wait()
     return out

@@ -154,6 +154,16 @@ HG_API int hg_aggr_groups(int64_t num_nodes, int64_t ngroup, const int32_t *d_ke
                           const float *d_s2, const float *d_a_out, const float *d_a_in,
                           float *d_Y, int32_t F, int32_t flags, int device, void *stream);
 
+/* Host <-> device staging of a COLUMN SLAB of a row-major fp32 matrix, asynchronous on `stream`
+ * (cudaMemcpy2DAsync; the host side should be pinned).  The aggregation never mixes feature columns
+ * (hgnnaggr_cuda.cu:21,34,44), so a host caller with a wide matrix uploads, aggregates and downloads
+ * it slab by slab and the PCIe copies of neighbouring slabs overlap in both directions; the reference
+ * has no host-buffer entry point (its extension takes device tensors, hgnnaggr.cc:122-129).
+ *   to_device != 0:  dst = device [nrow, ncol] (dense),  src = host [nrow, ld_host], columns col0..col0+ncol
+ *   to_device == 0:  dst = host [nrow, ld_host] columns col0..,  src = device [nrow, ncol] (dense) */
+HG_API int hg_copy_columns(void *dst, const void *src, int64_t nrow, int64_t ncol, int64_t ld_host,
+                           int64_t col0, int32_t to_device, int device, void *stream);
+
 /* ------------------------------------------------------------------------- *
  * The two stages as separate launches, for the vertex/hyperedge-PARTITIONED multi-GPU path
  * (new capability; the reference is single-GPU).  Rows of the CSR are the BOUNDARY hyperedges

@@ -426,15 +426,22 @@ def test_host_pipeline_matches_device_path(cuda_device):
     d, hg = _graph("mini_rep3", cuda_device)
     plan = ops.get_plan(hg.group_key, hg.group_row, hg.group_start, hg.group_end, hg.H_T_colind,
                         hg.num_nodes, hg.num_edges)
-    pipe = ops.HostPipeline(plan)
+    pipe = ops.HostPipeline(plan)           # wide matrices go up and down in column slabs of 128
     outs, wants = [], []
-    for F in (8, 32, 128):
+    for F in (8, 32, 128, 200, 300):
         X = torch.randn(hg.num_nodes, F, generator=torch.Generator().manual_seed(F)).pin_memory()
         outs.append(pipe.submit(X, None, s1=hg.degE, a_out=hg.degV))
         wants.append(orc.c_aggr_formula(d["H_T_csrptr"], d["H_T_colind"], X, s1=d["degE"], a_out=d["degV"]))
     pipe.wait()
     for o, w in zip(outs, wants):
         assert not o.is_cuda and orc.rel_err(o.numpy(), w) < TOL
+    X = torch.randn(hg.num_nodes, 72)       # pageable host memory, slabs of 32 columns with a ragged tail
+    whole = ops.HostPipeline(plan, col_slab=0).submit(X, None, s1=hg.degE, a_out=hg.degV)
+    slabs = ops.HostPipeline(plan, col_slab=32)
+    sl = slabs.submit(X, None, s1=hg.degE, a_out=hg.degV)
+    slabs.wait()
+    torch.cuda.synchronize()
+    assert orc.rel_err(sl.numpy(), whole.numpy()) < TOL
     X = torch.randn(hg.num_nodes, 16)
     assert orc.rel_err(ops.aggregate_host(plan, X, s1=hg.degE, a_out=hg.degV).numpy(),
                        orc.c_aggr_formula(d["H_T_csrptr"], d["H_T_colind"], X, s1=d["degE"], a_out=d["degV"])) < TOL

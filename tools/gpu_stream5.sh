@@ -1,4 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python tools/tune.py --force-stream --tag kv --sweep ";OCC=2;OCC=2,PIPE=1;OCC=2,L=128;OCC=2,ONLY=1;OCC=2,ONLY=2;OCC=2,SW=16;OCC=2,PIPE=1,SW=16" > gpurun_out/st_tune11.log 2>&1
-cat gpurun_out/st_tune11.log
+timeout 900 python -m pytest tests -m gpu -x -q -k "stream_form or kernel_form" > gpurun_out/st_pytest3.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/st_pytest3.log
+tail -3 gpurun_out/st_pytest3.log
+timeout 600 python tools/tune.py --tag static --sweep "STATIC=0;;OCC=4;L=16;L=16,OCC=4;L=48;L=64;ONLY=1;ONLY=2;OCC=4,ONLY=1;OCC=4,ONLY=2" > gpurun_out/st_tune13.log 2>&1
+cat gpurun_out/st_tune13.log

@@ -35,6 +35,66 @@ __global__ void __launch_bounds__(256) lean(const int *__restrict__ ind, long lo
   }
 }
 
+// same traffic, but every warp owns BLOCKS of `BLK` consecutive positions claimed from a global counter (the
+// work distribution of the library's stream kernel) instead of a fine round-robin interleave of all warps
+template <int F, int PER, int BLK, int UNR>
+__global__ void __launch_bounds__(256) lean_blocks(const int *__restrict__ ind, long long n, const float *__restrict__ src,
+                                                   float *__restrict__ dst, int *counter) {
+  constexpr int V = F / 128;
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(counter, 1);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    const long long p0 = (long long)t * BLK;
+    if (p0 >= n) break;
+    float4 s[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) s[j] = make_float4(0, 0, 0, 0);
+    for (long long p = p0; p < p0 + BLK && p + UNR <= n; p += UNR) {
+      int v[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) v[u] = __ldg(ind + p + u);
+      float4 x[UNR][V];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u)
+#pragma unroll
+        for (int j = 0; j < V; ++j) x[u][j] = __ldg(reinterpret_cast<const float4 *>(src + (size_t)v[u] * F) + lane + 32 * j);
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) { s[j].x += x[u][j].x; s[j].y += x[u][j].y; s[j].z += x[u][j].z; s[j].w += x[u][j].w; }
+        if ((u + 1) % PER == 0) {
+#pragma unroll
+          for (int j = 0; j < V; ++j) {
+            float *o = dst + (size_t)((p + u) / PER) * F + (lane + 32 * j) * 4;
+            asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(o), "f"(s[j].x), "f"(s[j].y), "f"(s[j].z), "f"(s[j].w) : "memory");
+            s[j] = make_float4(0, 0, 0, 0);
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int F, int PER, int BLK, int UNR>
+void run_blocks(const char *name, const int *d_ind, long long n, const float *src, float *dst, int *counter) {
+  for (int bps : {2, 3, 4, 6, 8}) {
+    int g = 148 * bps;
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    float tot = 0;
+    for (int it = 0; it < 6; ++it) {
+      CK(cudaMemset(counter, 0, 4));
+      cudaEventRecord(a);
+      lean_blocks<F, PER, BLK, UNR><<<g, 256>>>(d_ind, n, src, dst, counter);
+      cudaEventRecord(b); CK(cudaDeviceSynchronize());
+      float ms; cudaEventElapsedTime(&ms, a, b);
+      if (it) tot += ms;
+    }
+    printf("%-8s F=%3d per=%d blocks of %d, %d rows in flight, %d CTAs/SM  %8.1f us\n", name, F, PER, BLK, UNR, bps, tot / 5 * 1e3);
+  }
+}
+
 template <int F, int PER, int STREAM>
 void run(const char *name, const int *d_ind, long long n, const float *src, float *dst, size_t src_rows) {
   for (int bps : {2, 3, 4, 6, 8}) {
@@ -74,6 +134,11 @@ int main(int argc, char **argv) {
   CK(cudaMemset(X, 0, (size_t)N * maxF * 4)); CK(cudaMemset(Y, 0, (size_t)N * maxF * 4));
   printf("nnz=%lld N=%d M=%d\n", nnz, N, M);
   // stage A: gather X rows (vertex ids), 4 per stored Xe row; stage B: gather Xe rows (hyperedge ids), 2 per stored Y row
+  int *counter; CK(cudaMalloc(&counter, 4));
+  run_blocks<128, 4, 64, 4>("A-blk", d, nnz, X, Y, counter);
+  run_blocks<128, 4, 64, 8>("A-blk", d, nnz, X, Y, counter);
+  run_blocks<128, 4, 16, 8>("A-blk", d, nnz, X, Y, counter);
+  run_blocks<128, 2, 64, 8>("B-blk", db, nnz, X, Y, counter);
   run<128, 4, 0>("A", d, nnz, X, Y, N);
   run<128, 2, 1>("B", db, nnz, X, Y, M);
   run<128, 2, 0>("B", db, nnz, X, Y, M);

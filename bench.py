@@ -268,7 +268,8 @@ def run_ours(args, rank, world, local_rank):
                            heavy_hyperedges=plan.nheavy_edges, segments=plan.nseg),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "hg_aggr_forward per F (F<=128: pull_kernel phase A + phase B; F>=256: persistent fused_kernel), "
+                         "kernel": "hg_aggr_forward per F = stream form: stream_kernel stage A (X -> Xe over balancer segments) + "
+                                   "stage B (Xe -> Y over vertices), two launches per call, "
                                    "CUDA events around each C-ABI call",
                          "algorithmic_bytes_per_step": bytes_step, "sweep": sweep},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": io_bytes, "d2h_bytes_per_step": io_bytes,

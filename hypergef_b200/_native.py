@@ -40,6 +40,9 @@ SIGNATURES = {
     "hg_csr_build_host": [_i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _pi64],
     "hg_csr_build_dev": [_i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _pi64, _int, _vp],
     "hg_degree_scale_dev": [_i64, _vp, _vp, _f32, _int, _vp, _int, _vp],
+    "hg_mtx_open": [C.c_char_p, C.POINTER(_vp), _pi64, _pi64, _pi64],
+    "hg_mtx_fill": [_vp, _vp, _vp],
+    "hg_mtx_close": [_vp],
     "hg_plan_create": [C.POINTER(_vp), _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _int, _vp],
     "hg_plan_destroy": [_vp],
     "hg_plan_info": [_vp, _pi64, _pi64, _pi64, _pi32],

@@ -91,6 +91,19 @@ HG_API int hg_degree_scale_dev(int64_t nrow, const int32_t *d_indptr, const floa
                                void *stream);
 
 /* ------------------------------------------------------------------------- *
+ * MatrixMarket (.mtx) incidence reader (host).  Replaces read_mtx_file
+ * (include/dataloader/dataloader.hpp:22-104): coordinate format, values dropped, 0-based,
+ * `symmetric` mirrored and de-duplicated, coordinates sorted row-major; rows = vertices,
+ * columns = hyperedges.  open -> (sizes) -> fill -> close; the int64 pairs feed hg_csr_build_*.
+ * HG_EINVAL for a missing / malformed file (the reference calls exit()), HG_EGRAPH for an
+ * entry outside the declared shape (the reference stores it unchecked).
+ * ------------------------------------------------------------------------- */
+typedef struct hgMtx hgMtx;
+HG_API int hg_mtx_open(const char *path, hgMtx **mtx, int64_t *nrow, int64_t *ncol, int64_t *nnz);
+HG_API int hg_mtx_fill(const hgMtx *mtx, int64_t *h_rows, int64_t *h_cols);
+HG_API int hg_mtx_close(hgMtx *mtx);
+
+/* ------------------------------------------------------------------------- *
  * Aggregation plan: everything derived once from the balancer output so that the
  * per-call path is a single fused launch.  Borrowed pointers (d_key .. d_t_indices)
  * must outlive the plan.  Validates every index (HG_EGRAPH).

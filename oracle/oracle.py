@@ -362,3 +362,17 @@ def rel_err(got, want64) -> float:
     want64 = np.asarray(want64, dtype=np.float64)
     scale = max(float(np.abs(want64).max()) if want64.size else 0.0, 1e-30)
     return float(np.abs(got - want64).max() / scale) if want64.size else 0.0
+
+
+def ref_read_mtx(path):
+    """The reference's own MatrixMarket loader (include/dataloader/dataloader.hpp:22-104), compiled in place:
+    ``(nrow, ncol, indptr, indices, rowind)``.  Only for well-formed files -- it calls exit() otherwise."""
+    lib_ = ref_lib()
+    nrow, ncol, nnz = C.c_int(), C.c_int(), C.c_int()
+    lib_.ref_read_mtx(os.fsencode(path), C.byref(nrow), C.byref(ncol), C.byref(nnz))
+    indptr = np.empty(nrow.value + 1, np.int32)
+    indices = np.empty(nnz.value, np.int32)
+    rowind = np.empty(nnz.value, np.int32)
+    lib_.ref_read_mtx_fetch(indptr.ctypes.data_as(C.c_void_p), indices.ctypes.data_as(C.c_void_p),
+                            rowind.ctypes.data_as(C.c_void_p))
+    return nrow.value, ncol.value, indptr, indices, rowind

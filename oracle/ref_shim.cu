@@ -9,6 +9,7 @@
 //   ref_hyperaggr_host -> util::hyperaggr_reference_host   include/util/check.cuh:82-114
 //   ref_spmm_host      -> util::spmm_reference_host        include/util/check.cuh:60-79
 //   ref_weight_grad    -> util::hgnnbp_reference_host      include/util/check.cuh:116-143
+//   ref_read_mtx       -> read_mtx_file                     include/dataloader/dataloader.hpp:22-104
 //   ref_lab_full_gpu   -> HyperGAggr_Edgefused_Balance_Full_Kernel{,_sf} / _Shm_Kernel
 //                         include/hgnnAgg.cuh:98-276, launched with the grid/block
 //                         geometry of HyperGAggr_device (:985-1017) -- the reference's own
@@ -21,9 +22,24 @@
 
 namespace {
 std::vector<int> g_key, g_row, g_st, g_ed;
+std::vector<int> g_mtx_indptr, g_mtx_indices, g_mtx_rowind;
 }
 
 extern "C" {
+
+// The reference's MatrixMarket loader (exits the process on a malformed file: only call it on good ones).
+int ref_read_mtx(const char *path, int *nrow, int *ncol, int *nnz) {
+  g_mtx_indptr.clear(); g_mtx_indices.clear(); g_mtx_rowind.clear();
+  read_mtx_file(path, *nrow, *ncol, *nnz, g_mtx_indptr, g_mtx_indices, g_mtx_rowind);
+  return 0;
+}
+
+int ref_read_mtx_fetch(int *indptr, int *indices, int *rowind) {
+  std::copy(g_mtx_indptr.begin(), g_mtx_indptr.end(), indptr);
+  std::copy(g_mtx_indices.begin(), g_mtx_indices.end(), indices);
+  std::copy(g_mtx_rowind.begin(), g_mtx_rowind.end(), rowind);
+  return 0;
+}
 
 // Runs the reference balancer once and caches the vectors; sizes via out params.
 int ref_balance_run(int nrow, int part, const int *indptr, long long *nkey, long long *ngroup) {

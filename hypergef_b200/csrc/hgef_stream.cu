@@ -1,32 +1,32 @@
-// hgef_stream.cu -- the STREAM form of the fused aggregation: both stages as lean row streams,
-// optionally in ONE persistent launch with the hyperedge features handed over through the L2.
+// hgef_stream.cu -- the STREAM form of the fused aggregation: both stages as lean, register-only row streams
+// (the default for graphs whose Y exceeds the L2); optionally in ONE persistent launch.
 //
-// What the round-1 profiles said (profiles/r01_ncu_prof_r1_pull_f128.txt): the gather-only two-phase
-// form has ideal DRAM traffic but spends ~45 warp instructions per gathered row (tile staging in
-// shared memory, cp.async ring, per-unit bookkeeping for units of 2-4 rows) at 16 resident warps per
-// SM: issue-bound at half the DRAM rate.  A trivially lean gather of the same address stream
-// saturates DRAM once >= 128 KB of row loads are in flight per SM (tools/replay.cu).
+// What the profiles of the earlier forms said (profiles/r01_ncu_prof_r1_pull_f128.txt): the gather-only
+// two-phase form has ideal DRAM traffic but spends ~45 warp instructions per gathered row (tile staging in
+// shared memory, cp.async ring, per-unit bookkeeping for units of 2-4 rows) at 16 resident warps per SM.
 //
 // Here everything a row needs is precomputed once per graph into a ROW PROGRAM (hg_plan_create):
-//     src[p]  row to gather at position p, bit31 = "last member of its unit"
-//     dst[p]  output row of the unit that owns p, bit31 = "heavy: reduce, do not store"
+//     src[p]  row to gather at position p
+//     dst[p]  output row of the unit that owns p; bit31 = "last member of its unit" (store now),
+//             bit30 = "heavy: reduce into the pre-zeroed row, do not store"
 //     run[r]  first position of base run r (unit-aligned, ~kL0 positions each)
-// for stage A (units = balancer segments of H^T, gather X, output Xe) and stage B (units = vertices,
-// gather Xe, output Y).  A sub-warp of SW lanes streams one run: 32 positions' src/dst words are
-// held one per lane and handed out by shuffles, kVec 128-bit row loads per lane are issued
-// back to back straight into registers (no shared memory at all), and a unit end costs one scale and
-// one 128-bit store per lane.  ~12-15 warp instructions per row, 24-32 resident warps per SM.
+// for stage A (units = balancer segments of H^T, gather X, output Xe) and stage B (units = vertices ordered
+// by their last hyperedge, gather Xe, output Y).  Warps claim items of a few runs from one counter.  A sub-warp
+// of SW lanes streams one run: the src / dst words of SW positions are held one per lane (the next chunk's
+// are prefetched) and handed out by shuffles; rows are loaded in half-batches into two alternating register
+// sets, half h + 1 issued before half h is consumed, so every lane has 4..8 row vectors in flight; a unit end
+// is one uniform test of a ballot mask and costs two shuffles, a scale and one 128-bit store per lane.  No
+// shared memory, no barriers, no atomics but the ticket (and red.v4 for heavy hyperedges).  Per-stage kernels
+// take every array base from the constant bank: 64 registers at one vector per lane.
+// What bounds it: DRAM at >= 1 KB rows (94-96 % of the copy peak, 1.3x the algorithmic
+// traffic because Xe makes a round trip); below that, how much the L2 serves at 24-32 warps per SM.
 //
-// FUSED launch: stage-B units are ordered by the LAST hyperedge they depend on, both stages are cut
-// into items and merged into one ticket sequence in which a B item follows the A items it needs
-// (plus a lag); warps claim tickets in order from one counter, A items publish per-block completion
-// counts (release), B items wait on a monotone per-warp watermark (normally already satisfied).
-// Xe rows are therefore consumed while still L2-resident, the Xe read never reaches DRAM, and there
-// is no ramp-down / ramp-up between the stages.  Deadlock-free: an item is only claimed by a running
-// warp, tickets are claimed in order, a B item waits only for A items with smaller tickets, A items
-// never wait; waits are bounded (give-up flag -> hg_plan_check).
-// Wide rows are processed as column SLABS (the ticket sequence repeated per slab) so that the set of
-// rows in flight, in bytes, stays below the L2 size.
+// FUSED launch (STAGE = -1, HGEF_ST_FUSED=1; measured slower, kept for A/B): both stages are cut into items
+// and merged into one ticket sequence in which a B item follows the A items it needs (plus a lag); warps claim
+// tickets in order, A items publish per-block completion counts (release), B items wait on a monotone
+// per-warp watermark.  Deadlock-free: an item is only claimed by a running warp, tickets are claimed in
+// order, a B item waits only for A items with smaller tickets, A items never wait; waits are bounded
+// (give-up flag -> hg_plan_check).  Wide rows (> 512 floats) are processed as column SLABS.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 

@@ -323,6 +323,38 @@ def test_stream_form_configurations(shape, replicas, cuda_device, monkeypatch):
             assert orc.rel_err(_np(out), want) < TOL
 
 
+@pytest.mark.parametrize("form", ["two_pass", "stream", "stream_fused", "fused", "pull"])
+def test_cuda_graph_capture_and_replay(form, cuda_device, monkeypatch):
+    """Every kernel form is capture-safe after one eager warm-up call (the first call of a plan may allocate its
+    scratch): a captured aggregation replays correctly on new contents of the same input buffer."""
+    flags = {"two_pass": _native.HG_TWO_PASS, "stream": _native.HG_FORCE_STREAM, "stream_fused": _native.HG_FORCE_STREAM,
+             "fused": _native.HG_FORCE_FUSED, "pull": _native.HG_FORCE_PULL}[form]
+    if form == "stream_fused":
+        monkeypatch.setenv("HGEF_ST_FUSED", "1")
+    data = synth.make_shape("pubmed", replicas=2, seed=5)
+    hg = HyperGraph(data, cuda_device, data.dataset)
+    plan = ops.get_plan(hg.group_key, hg.group_row, hg.group_start, hg.group_end, hg.H_T_colind, hg.num_nodes,
+                        hg.num_edges)
+    F = 64
+    X = torch.randn(hg.num_nodes, F, device=cuda_device)
+    Y = torch.empty_like(X)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        ops.aggregate(plan, X, s1=hg.degE, a_out=hg.degV, out=Y, flags=flags)      # warm-up: allocations happen here
+        side.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            ops.aggregate(plan, X, s1=hg.degE, a_out=hg.degV, out=Y, flags=flags)
+    for seed in (1, 2):
+        X.copy_(torch.randn(hg.num_nodes, F, device=cuda_device, generator=torch.Generator(device=cuda_device).manual_seed(seed)))
+        Y.fill_(float("nan"))
+        graph.replay()
+        torch.cuda.synchronize()
+        want = ops.aggregate(plan, X, s1=hg.degE, a_out=hg.degV, flags=_native.HG_TWO_PASS)
+        assert ((Y - want).abs().max() / want.abs().max()).item() < TOL, (form, seed)
+    plan.check()
+
+
 # ------------------------------------------------------------------ error behaviour
 def test_errors_raise_instead_of_aborting(cuda_device):
     d, hg = _graph("mini", cuda_device)

@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("HGEF_B200_LIB") or os.path.join(_HERE, "libhgef_b200.
 
 HG_OK, HG_EINVAL, HG_ECUDA, HG_ENOMEM, HG_EEMPTY, HG_EGRAPH = range(6)
 HG_ACCUMULATE, HG_FORCE_SCALAR, HG_TWO_PASS, HG_FORCE_FUSED, HG_FORCE_PULL, HG_FORCE_STREAM = 1, 4, 8, 16, 32, 64
+HG_FORCE_RING = 128
 
 
 class HgefBuildError(ImportError):
@@ -33,6 +34,7 @@ _pi32 = C.POINTER(C.c_int32)
 SIGNATURES = {
     "hg_abi_version": [],
     "hg_device_cc": [_int],
+    "hg_tune_set": [C.c_char_p, _i32, _i32],
     "hg_balance_count_host": [_i64, _vp, _i32, _pi64, _pi64],
     "hg_balance_fill_host": [_i64, _vp, _i32, _vp, _vp, _vp, _vp],
     "hg_balance_count_dev": [_i64, _vp, _i32, _pi64, _pi64, _int, _vp],

@@ -18,7 +18,7 @@
 //
 // The literal group schedule of the reference (hgnnaggr_cuda.cu:14-47) is kept as
 // hg_aggr_groups: same device code, one warp per balancer group.
-#include "hgef_aggr.cuh"
+#include "hgef_stream.cuh"
 
 namespace hg {
 bool fused_available(const hgPlan *plan, int F, bool force);
@@ -218,6 +218,7 @@ int hg_plan_check(hgPlan *plan, void *stream) {
   HG_CUDA_TRY(cudaStreamSynchronize(s));
   HG_CUDA_TRY(cudaGetLastError());
   if (int rc = stream_check(plan, s)) return rc;
+  if (int rc = ring_check(plan, s)) return rc;
   return fused_check(plan, s);
 }
 
@@ -235,8 +236,16 @@ int hg_aggr_forward(hgPlan *plan, const float *d_X, const float *d_s1, const flo
   cudaStream_t s = (cudaStream_t)stream;
   const bool vec4 = F % 4 == 0 && !(flags & HG_FORCE_SCALAR) && aligned16(d_X) && aligned16(d_Y);
   const bool vec = vec4 && F <= 512;
-  // stream form: both stages as lean row streams, one persistent launch (hgef_stream.cu)
-  const bool use_stream = vec4 && !(flags & (HG_ACCUMULATE | HG_TWO_PASS | HG_FORCE_FUSED | HG_FORCE_PULL)) &&
+  // ring form: one persistent launch, TMA row ring, hyperedge features through the L2 (hgef_ring.cu)
+  const bool use_ring = vec4 && !(flags & (HG_ACCUMULATE | HG_TWO_PASS | HG_FORCE_FUSED | HG_FORCE_PULL | HG_FORCE_STREAM)) &&
+                        ring_available(plan, F, (flags & HG_FORCE_RING) != 0);
+  if (use_ring) {
+    Args pa{};
+    pa.X = d_X; pa.s1 = d_s1; pa.s2 = d_s2; pa.a_out = d_a_out; pa.a_in = d_a_in; pa.Y = d_Y; pa.F = F;
+    return launch_ring(plan, pa, s);
+  }
+  // stream form: both stages as lean register-only row streams, two launches (hgef_stream.cu)
+  const bool use_stream = vec4 && !(flags & (HG_ACCUMULATE | HG_TWO_PASS | HG_FORCE_FUSED | HG_FORCE_PULL | HG_FORCE_RING)) &&
                       stream_available(plan, F, (flags & HG_FORCE_STREAM) != 0);
   if (use_stream) {
     Args pa{};

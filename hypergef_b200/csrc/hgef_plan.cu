@@ -19,6 +19,7 @@
 namespace hg {
 int build_stream(hgPlan *p, cudaStream_t s);
 void stream_free(hgPlan *p);
+void ring_free(hgPlan *p);
 namespace {
 
 enum : int { kBadIndex = 1, kBadKey = 2, kBadGroup = 4, kNotCanonical = 8 };
@@ -406,6 +407,7 @@ int hg_plan_destroy(hgPlan *p) {
   cudaFree(p->ctrl);
   cudaFree(p->scratch);
   stream_free(p);
+  ring_free(p);
   delete p;
   return HG_OK;
 }

@@ -46,6 +46,19 @@ struct hgPlan {
   static constexpr int kMaxSched = 8;
   StreamSched st_sched[kMaxSched];
   int st_nsched = 0;
+  // ring form (hgef_ring.cu): hyperedges ordered by their last stage-B read position (the discard order), and
+  // merged A / B / discard ticket orders for one item size and pair of lags
+  int32_t *rg_dperm = nullptr, *rg_dlast = nullptr;
+  int32_t rg_ready = 0;
+  struct RingSched {
+    int bpi, lagB, lagC, nslab, discard;
+    int32_t GA, GB, GC, nblkA, nblkB, nitem;
+    int4 *items;                  // per ticket: {first position, end position, kind | index << 2, blocks needed}
+    int32_t *ctrl;                // kCtrlHdr + nslab * (nblkA + nblkB) words
+  };
+  RingSched rg_sched[kMaxSched];
+  int rg_nsched = 0;
+  int32_t *rg_last_ctrl = nullptr;
   // scratch: partial hyperedge features of heavy hyperedges, [nheavy_edges, F]; L2-resident
   float *scratch = nullptr;
   size_t scratch_floats = 0;

@@ -1,0 +1,27 @@
+// hgef_stream.cuh -- what the stream form (hgef_stream.cu) and the ring form (hgef_ring.cu) share: the
+// layout of a row program and of the control words.
+#pragma once
+
+#include "hgef_aggr.cuh"
+
+namespace hg {
+
+// dst word of a row program: bit31 = last member of its unit (store now), bit30 = heavy (reduce into the
+// pre-zeroed row), low 30 bits = output row
+constexpr uint32_t kEnd = 0x80000000u, kHeavy = 0x40000000u, kIdMask = 0x3fffffffu, kRowMask = kIdMask;
+constexpr int kL0 = 16;      // positions per base run (unit-aligned)
+constexpr int kBlk = 8;      // items per completion counter
+constexpr int kCtrlHdr = 8;  // ctrl[0] ticket counter, ctrl[1] give-up flag, ctrl[8..] completion counts
+
+// process-wide tuning table (hg_tune_set); -1 / absent = the built-in default
+int tune_get(const char *name, int dflt);
+
+int ensure_xe(hgPlan *plan, int F, cudaStream_t s);
+
+// ring form (hgef_ring.cu)
+bool ring_available(const hgPlan *plan, int F, bool force);
+int launch_ring(hgPlan *plan, const dev::Args &a, cudaStream_t s);
+void ring_free(hgPlan *plan);
+int ring_check(hgPlan *plan, cudaStream_t s);
+
+}  // namespace hg

@@ -34,7 +34,7 @@ from . import _native
 __all__ = [
     "hgnnaggr", "hgnnaggr_mean", "hgnnaggr_max", "unignnaggrdeg", "unignnaggr",
     "set_backward_mode", "get_backward_mode", "aggregate", "aggregate_host", "HostPipeline", "Plan", "get_plan", "clear_plan_cache",
-    "launch_count",
+    "launch_count", "tune",
 ]
 
 DEFAULT_FLAGS = 0       # OR-ed into every hg_aggr_forward call (tests force one kernel form with it)
@@ -56,6 +56,14 @@ def get_backward_mode() -> str:
 
 def launch_count() -> int:
     return _LAUNCHES
+
+
+def tune(**knobs) -> None:
+    """Override launch-geometry defaults of the aggregation kernels (``hg_tune_set``); ``None`` restores one.
+
+    Measurement / test hook, e.g. ``tune(ring_kb=96, ring_lag_b=600)``; names are listed in DESIGN.md section 3."""
+    for name, value in knobs.items():
+        _native.call("hg_tune_set", name.encode(), 0 if value is None else int(value), 1 if value is None else 0)
 
 
 # ----------------------------------------------------------------------------

@@ -48,6 +48,10 @@ HG_API const char *hg_last_error(void);
 HG_API int hg_abi_version(void);
 /* Compute capability of `device` as major*10+minor, or <0 on error. */
 HG_API int hg_device_cc(int device);
+/* Process-wide override of one launch-geometry default of the aggregation kernels (ring depth, item size,
+ * lags, eviction hints ...: the names are listed in DESIGN.md section 3); clear != 0 restores the default.
+ * For measurement and tests: the reference fixes its geometry at compile time (hgnnaggr_cuda.cu:376-404). */
+HG_API int hg_tune_set(const char *name, int32_t value, int32_t clear);
 
 /* ------------------------------------------------------------------------- *
  * Balancer.  Replaces balance_schedule.balancer, HyperGsys/balancer.py:15-33
@@ -136,9 +140,11 @@ enum {
   HG_FORCE_FUSED = 16,   /* always the single persistent scatter launch */
   HG_FORCE_PULL = 32,    /* always the gather-only two-phase form with shared-memory staging (Xe through L2/HBM,
                             no reductions; the earlier form, kept for A/B) */
-  HG_FORCE_STREAM = 64   /* always the stream form: both stages as register-only row streams, one persistent launch
-                            with the hyperedge features handed over through the L2 (the form chosen when Y exceeds
-                            the L2) */
+  HG_FORCE_STREAM = 64,  /* always the stream form: both stages as register-only row streams, two launches, the
+                            hyperedge features make a round trip through HBM */
+  HG_FORCE_RING = 128    /* always the ring form: both stages in one persistent launch, rows moved by TMA bulk copies
+                            into a shared-memory ring, hyperedge features handed over through the L2 and discarded
+                            there (the form chosen for rows >= 512 B when Y exceeds the L2) */
 };
 
 /* ------------------------------------------------------------------------- *

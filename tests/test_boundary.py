@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_error_channel():
     lib = _native.lib()
-    assert lib.hg_abi_version() == 1
+    assert lib.hg_abi_version() == 2
     n = ctypes.c_int64()
     rc = lib.hg_balance_count_host(1, None, 3, ctypes.byref(n), ctypes.byref(n))
     assert rc == _native.HG_EINVAL and b"csrptr" in lib.hg_last_error()

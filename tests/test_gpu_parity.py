@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-5
 
 
-@pytest.fixture(params=["auto", "fused", "two_pass", "pull", "stream", "stream2"])
+@pytest.fixture(params=["auto", "fused", "two_pass", "pull", "stream", "stream2", "ring"])
 def kernel_form(request):
     """Run a test with the library's own choice of kernel form, then with each form forced
     (the large-graph forms are only chosen on their own when Y exceeds the L2).  "stream" is the
@@ -27,7 +27,7 @@ def kernel_form(request):
     import os
     ops.DEFAULT_FLAGS = {"auto": 0, "fused": _native.HG_FORCE_FUSED, "two_pass": _native.HG_TWO_PASS,
                          "pull": _native.HG_FORCE_PULL, "stream": _native.HG_FORCE_STREAM,
-                         "stream2": _native.HG_FORCE_STREAM}[request.param]
+                         "stream2": _native.HG_FORCE_STREAM, "ring": _native.HG_FORCE_RING}[request.param]
     if request.param in ("stream", "stream2"):
         os.environ["HGEF_ST_FUSED"] = "1" if request.param == "stream" else "0"
     yield request.param
@@ -323,12 +323,57 @@ def test_stream_form_configurations(shape, replicas, cuda_device, monkeypatch):
             assert orc.rel_err(_np(out), want) < TOL
 
 
-@pytest.mark.parametrize("form", ["two_pass", "stream", "stream_fused", "fused", "pull"])
+RING_KNOBS = ("ring_consumers", "ring_ctas", "ring_qd", "ring_chunk", "ring_kb", "ring_item_kb", "ring_lag_b", "ring_lag_c",
+              "ring_discard", "ring_pol_x", "ring_pol_xe_w", "ring_pol_xe_r", "ring_pol_y")
+
+
+@pytest.mark.parametrize("shape,replicas", [("pubmed", 3), ("walmart", 1), ("dblp", 2)])
+def test_ring_form_configurations(shape, replicas, cuda_device):
+    """The ring form (one persistent launch: TMA row ring, A / B / discard items in one ticket order) under
+    every geometry knob -- consumers, ring size, chunk length, item size, lags down to 0 (dependencies
+    really wait), discard on / off, eviction hints -- forward and transposed, EVERY feature length against
+    the fp64 C oracle.  Results are bit-identical run to run where the graph has no heavy hyperedge."""
+    data = synth.make_shape(shape, replicas=replicas, seed=3)
+    hg = HyperGraph(data, cuda_device, data.dataset)
+    N, M = hg.num_nodes, hg.num_edges
+    plan = ops.get_plan(hg.group_key, hg.group_row, hg.group_start, hg.group_end, hg.H_T_colind, N, M)
+    W = torch.rand(M, device=cuda_device) + 0.5
+    ptr, ind = _np(hg.H_T_csrptr), _np(hg.H_T_colind)
+    combos = [dict(), dict(ring_lag_b=0, ring_lag_c=0), dict(ring_consumers=3, ring_ctas=1, ring_kb=160),
+              dict(ring_consumers=15, ring_qd=2, ring_chunk=2, ring_item_kb=8),
+              dict(ring_chunk=32, ring_item_kb=256, ring_kb=64), dict(ring_discard=0, ring_lag_b=1000000),
+              dict(ring_kb=16, ring_item_kb=4, ring_lag_b=3, ring_lag_c=1),
+              dict(ring_pol_x=0, ring_pol_xe_w=0, ring_pol_xe_r=1, ring_pol_y=0, ring_ctas=3, ring_kb=48),
+              dict(ring_consumers=1, ring_qd=1, ring_chunk=5, ring_ctas=4, ring_kb=32)]
+    try:
+        for F in (4, 20, 32, 64, 100, 128, 256, 384, 512, 640, 1056):
+            X = torch.randn(N, F, device=cuda_device)
+            s_edge = _np(hg.degE).ravel() * _np(W)
+            want = orc.c_aggr_formula(ptr, ind, X.cpu(), s1=s_edge, a_out=_np(hg.degV))
+            want_t = orc.c_aggr_formula(ptr, ind, X.cpu(), s1=s_edge, a_in=_np(hg.degV))
+            for knobs in combos:
+                ops.tune(**{k: None for k in RING_KNOBS})
+                ops.tune(**knobs)
+                out = torch.full((N, F), float("nan"), device=cuda_device)
+                ops.aggregate(plan, X, s1=hg.degE, s2=W, a_out=hg.degV, out=out, flags=_native.HG_FORCE_RING)
+                plan.check()
+                assert orc.rel_err(_np(out), want) < TOL, (shape, F, knobs)
+                out_t = ops.aggregate(plan, X, s1=hg.degE, s2=W, a_in=hg.degV, flags=_native.HG_FORCE_RING)
+                assert orc.rel_err(_np(out_t), want_t) < TOL, (shape, F, knobs, "transposed")
+                if plan.nheavy_edges == 0:
+                    again = ops.aggregate(plan, X, s1=hg.degE, s2=W, a_out=hg.degV, flags=_native.HG_FORCE_RING)
+                    assert torch.equal(again, out), (shape, F, knobs, "run-to-run")
+                plan.check()
+    finally:
+        ops.tune(**{k: None for k in RING_KNOBS})
+
+
+@pytest.mark.parametrize("form", ["two_pass", "stream", "stream_fused", "fused", "pull", "ring"])
 def test_cuda_graph_capture_and_replay(form, cuda_device, monkeypatch):
     """Every kernel form is capture-safe after one eager warm-up call (the first call of a plan may allocate its
     scratch): a captured aggregation replays correctly on new contents of the same input buffer."""
     flags = {"two_pass": _native.HG_TWO_PASS, "stream": _native.HG_FORCE_STREAM, "stream_fused": _native.HG_FORCE_STREAM,
-             "fused": _native.HG_FORCE_FUSED, "pull": _native.HG_FORCE_PULL}[form]
+             "fused": _native.HG_FORCE_FUSED, "pull": _native.HG_FORCE_PULL, "ring": _native.HG_FORCE_RING}[form]
     if form == "stream_fused":
         monkeypatch.setenv("HGEF_ST_FUSED", "1")
     data = synth.make_shape("pubmed", replicas=2, seed=5)
@@ -509,7 +554,8 @@ def test_ragged_and_degenerate_graphs(cuda_device):
             want = orc.c_aggr_formula(ptr, ind, X, s1=_np(hg.degE), a_out=_np(hg.degV))
             out = torch.full((N, F), float("nan"), device=cuda_device)
             plan = ops.get_plan(hg.group_key, hg.group_row, hg.group_start, hg.group_end, hg.H_T_colind, N, hg.num_edges)
-            for flags in (0, _native.HG_TWO_PASS, _native.HG_FORCE_FUSED, _native.HG_FORCE_PULL, _native.HG_FORCE_STREAM):
+            for flags in (0, _native.HG_TWO_PASS, _native.HG_FORCE_FUSED, _native.HG_FORCE_PULL, _native.HG_FORCE_STREAM,
+                          _native.HG_FORCE_RING):
                 ops.aggregate(plan, X.to(cuda_device), s1=hg.degE, a_out=hg.degV, out=out, flags=flags)
                 assert orc.rel_err(_np(out), want) < TOL or np.abs(want).max() == 0, (len(members), N, ngs, F, flags)
             plan.check()

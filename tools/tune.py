@@ -15,6 +15,7 @@ ap.add_argument("--two-pass", action="store_true")
 ap.add_argument("--force-fused", action="store_true")
 ap.add_argument("--force-pull", action="store_true")
 ap.add_argument("--force-stream", action="store_true")
+ap.add_argument("--force-ring", action="store_true")
 ap.add_argument("--tag", default="")
 ap.add_argument("--sweep", default="", help="semicolon-separated env configs K=V,K=V applied in-process (stream form knobs are read per call)")
 args = ap.parse_args()
@@ -24,14 +25,21 @@ hg = hgef.HyperGraph(data, dev, data.dataset)
 N, M, Z = hg.num_nodes, hg.num_edges, hg.H_T_colind.numel()
 plan = ops.get_plan(hg.group_key, hg.group_row, hg.group_start, hg.group_end, hg.H_T_colind, N, M)
 W = torch.ones(M, device=dev)
-flags = _native.HG_TWO_PASS if args.two_pass else (_native.HG_FORCE_FUSED if args.force_fused else (_native.HG_FORCE_PULL if args.force_pull else (_native.HG_FORCE_STREAM if args.force_stream else 0)))
+flags = _native.HG_TWO_PASS if args.two_pass else (_native.HG_FORCE_FUSED if args.force_fused else (_native.HG_FORCE_PULL if args.force_pull else (_native.HG_FORCE_STREAM if args.force_stream else (_native.HG_FORCE_RING if args.force_ring else 0))))
+TUNED = set()
 KNOBS = ("HGEF_ST_FUSED", "HGEF_ST_L", "HGEF_ST_LAG", "HGEF_ST_SLAB", "HGEF_ST_CTAS", "HGEF_ST_ONLY", "HGEF_ST_OCC", "HGEF_ST_CS", "HGEF_ST_SW", "HGEF_ST_PIPE")
 for cfg in (args.sweep.split(";") if args.sweep else [""]):
     for k in (KNOBS if args.sweep else ()):
         os.environ.pop(k, None)
+    ops.tune(**{k: None for k in TUNED})
+    TUNED.clear()
     for kv in filter(None, cfg.split(",")):
         k, v = kv.split("=")
-        os.environ[k if k.startswith("HGEF_") else "HGEF_ST_" + k] = v
+        if k.startswith("ring") or k.startswith("st_"):     # hg_tune_set knobs
+            ops.tune(**{k: int(v)})
+            TUNED.add(k)
+        else:
+            os.environ[k if k.startswith("HGEF_") else "HGEF_ST_" + k] = v
     out = []
     for F in [int(f) for f in args.features.split(",")]:
         X = torch.randn(N, F, device=dev); Y = torch.empty(N, F, device=dev)

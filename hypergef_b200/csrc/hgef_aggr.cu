@@ -210,6 +210,13 @@ int hg_plan_launches(const hgPlan *plan, int64_t *kernels) {
   return HG_OK;
 }
 
+int hg_plan_debug(hgPlan *plan, int32_t *h_out8, void *stream) {
+  HG_REQUIRE(plan != nullptr && h_out8 != nullptr, "plan_debug: NULL argument");
+  DeviceGuard guard(plan->device);
+  HG_REQUIRE(guard.ok(), "plan_debug: cannot select device %d", plan->device);
+  return ring_debug(plan, h_out8, (cudaStream_t)stream);
+}
+
 int hg_plan_check(hgPlan *plan, void *stream) {
   HG_REQUIRE(plan != nullptr, "plan_check: plan is NULL");
   DeviceGuard guard(plan->device);

@@ -14,19 +14,21 @@
 // ITEMS of ~32 KB of rows; a third item kind, DISCARD, lists the hyperedges whose last stage-B reader lies in
 // one block of B items.  All items are merged into one ticket order in which a B item follows the A items that
 // produce its hyperedge features (plus a lag) and a discard item follows the B items that read its rows.
-// One CTA = 1 producer warp + NC consumer warps:
-//   producer  claims tickets (three ahead: ticket -> item -> index words are prefetched, the words with
+// One CTA = 1 control warp + NC worker warps:
+//   control   claims tickets (three ahead: ticket -> item -> index words are prefetched, the words with
 //             cp.async), waits for an item's dependencies (completion counters, relaxed polls + one acquire
-//             fence), cuts the item into CHUNKS of <= `ch` rows ending at unit ends where possible, hands
-//             every chunk to a consumer through that consumer's descriptor queue and issues one
-//             cp.async.bulk (UBLKCP) per row into the ring, completing on the chunk's mbarrier.  Ring space is
-//             reclaimed in issue order through per-chunk "consumed" mbarriers.  Discard items are executed by
-//             the producer's own lanes.
-//   consumer  waits for a chunk's rows to land, adds them up from shared memory (one warp per chunk, 1 / 2 / 4
-//             128-bit vectors per lane), and at every unit end scales and stores the output row: Xe with an
-//             evict-last hint (heavy hyperedges: red.v4 into the pre-zeroed row), Y with evict-first.  A unit
-//             that continues into the next chunk stays with the same consumer, so the sum is carried in
-//             registers and its order is fixed.
+//             fence), cuts the item into CHUNKS of <= `ch` rows ending at unit ends where possible and hands
+//             every chunk to a worker through that worker's descriptor queue (mbarrier-guarded).  Discard
+//             items are executed by the control warp's own lanes.
+//   worker    issues one cp.async.bulk (UBLKCP) per row of its chunks into its OWN ring region, completing on
+//             the chunk's mbarrier, as far ahead as the ring allows; sums the rows of the oldest chunk from
+//             shared memory (1 / 2 / 4 128-bit vectors per lane) and at every unit end scales and stores the
+//             output row: Xe with an evict-last hint (heavy hyperedges: red.v4 into the pre-zeroed row), Y
+//             with evict-first.  A unit that continues into the next chunk stays with the same worker, so
+//             the sum is carried in registers and its order is fixed.  Why every worker issues its own
+//             copies: a bulk copy blocks its issuing warp for ~65 clocks and the copies of ONE warp are
+//             served at about one per 300 clocks whatever their size (profiles/r02_tma_probe.txt); only many
+//             issuing warps reach the DRAM rate (a single producer warp: 7x slower, measured).
 // Completion of an item = all its chunks consumed; the last contributor (shared-memory counter) releases it
 // with fence.release.gpu + a relaxed increment of the item block's global counter.
 // Deadlock freedom: tickets are claimed in order by running CTAs only; an item waits only for items with
@@ -42,7 +44,7 @@ using namespace dev;
 constexpr int kMaxP = 512;        // positions of an item whose index words are prefetched into shared memory
 constexpr int kIS = 8;            // items whose completion a CTA tracks at one time
 constexpr int kBig = 1 << 20;
-constexpr int kMaxEntries = 64;   // descriptor-queue entries per CTA (consumers x depth)
+constexpr int kMaxEntries = 96;   // descriptor-queue entries per CTA (workers x depth)
 constexpr int kStop = -1;
 enum { kKindA = 0, kKindB = 1, kKindC = 2 };
 enum { kPolNormal = 0, kPolFirst = 1, kPolLast = 2 };
@@ -60,11 +62,12 @@ struct RingArgs {
   int32_t niso, nitem, nslab, slabF, F;
   int32_t nblkA, nblkB, GA, GB;
   int32_t npos;                     // positions per stage (nnz)
-  int32_t rs;                       // ring slots (rows)
+  int32_t rs;                       // ring slots (rows) of one worker
   int32_t ch;                       // rows per chunk (<= 32)
-  int32_t qd;                       // descriptor-queue entries per consumer
+  int32_t qd;                       // descriptor-queue entries per worker
   int32_t track_b;                  // B items are counted too (discard items wait for them)
   int32_t pol_x, pol_xe_w, pol_xe_r, pol_y;
+  int32_t prof;                     // accumulate a clock breakdown in ctrl[2..7] (kilo-clocks; diagnostic)
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -134,57 +137,72 @@ __device__ __forceinline__ void sts_volatile(int *p, int v) {
   asm volatile("st.volatile.shared::cta.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
 
-// shared-memory layout (dynamic): ring | barriers | chunk headers | chunk words | prefetched words | item slots | fifo
-struct Layout {
-  uint32_t ring, full, empty, hdr, dstw, srcw, wbuf, icnt, iblk, fifo, total;
+struct Prof {   // diagnostic clock breakdown of one warp
+  long long t[3] = {0, 0, 0};
+  bool on;
+  __device__ __forceinline__ long long now() const { return on ? clock64() : 0; }
+  __device__ __forceinline__ void add(int i, long long t0) { if (on) t[i] += clock64() - t0; }
+  __device__ __forceinline__ void flush(int *ctrl, int base, int lane) {
+    if (on && lane == 0)
+      for (int i = 0; i < 3; ++i) atomicAdd(ctrl + base + i, (int)(t[i] >> 10));
+  }
 };
-__host__ __device__ inline Layout make_layout(int rs, int slot_bytes, int ne) {
+
+// shared-memory layout (dynamic): rings | barriers | chunk headers | chunk words | prefetched words | item slots
+struct Layout {
+  uint32_t ring, ready, data, empty, hdr, dstw, srcw, scw, wbuf, icnt, iblk, total;
+};
+__host__ __device__ inline Layout make_layout(int nc, int rsw, int slot_bytes, int ne, int ch) {
   Layout l;
   uint32_t o = 0;
-  l.ring = o; o += (uint32_t)rs * slot_bytes; o = (o + 127u) & ~127u;
-  l.full = o; o += ne * 8;
+  l.ring = o; o += (uint32_t)nc * rsw * slot_bytes; o = (o + 127u) & ~127u;
+  l.ready = o; o += ne * 8;
+  l.data = o; o += ne * 8;
   l.empty = o; o += ne * 8;
   o = (o + 15u) & ~15u;
   l.hdr = o; o += ne * 32;
-  l.dstw = o; o += ne * 32 * 4;
-  l.srcw = o; o += ne * 32 * 4;
+  l.dstw = o; o += ne * ch * 4;
+  l.srcw = o; o += ne * ch * 4;
+  l.scw = o; o += ne * ch * 8;            // output scale and gather-side weight of every position
   l.wbuf = o; o += 2 * 2 * kMaxP * 4;
   l.icnt = o; o += kIS * 4;
   l.iblk = o; o += kIS * 4;
-  l.fifo = o; o += ne * 4;
   l.total = (o + 15u) & ~15u;
   return l;
 }
 
-// marks an item complete: everything its consumers stored becomes visible before the count
+// marks an item complete: everything its workers stored becomes visible before the count
 __device__ __forceinline__ void complete_item(const RingArgs &ra, int *icnt, const int *iblk, int islot) {
   const int b = lds_volatile(iblk + islot);
+  asm volatile("fence.proxy.async.global;" ::: "memory");
   asm volatile("fence.release.gpu;" ::: "memory");
   red_inc_relaxed(ra.ctrl + kCtrlHdr + b);
   sts_volatile(icnt + islot, 0);
 }
 
 template <int VPL, bool HAS_WIN>
-__global__ void __launch_bounds__(512, 1) ring_kernel(const __grid_constant__ RingArgs ra) {
+__global__ void __launch_bounds__(544, 1) ring_kernel(const __grid_constant__ RingArgs ra) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int NC = (int)(blockDim.x >> 5) - 1;
-  const int QD = ra.qd;
+  const int QD = ra.qd, CH = ra.ch;
   const int NE = NC * QD;
+  const int rsw = ra.rs;                     // ring slots of ONE worker
   const uint32_t slot_bytes = (uint32_t)ra.slabF * 4u;
-  const Layout L = make_layout(ra.rs, (int)slot_bytes, NE);
+  const Layout L = make_layout(NC, rsw, (int)slot_bytes, NE, CH);
   const uint32_t s_base = smem_u32(smem);
   int4 *hdr = reinterpret_cast<int4 *>(smem + L.hdr);
   int32_t *dstw = reinterpret_cast<int32_t *>(smem + L.dstw);
   int32_t *srcw = reinterpret_cast<int32_t *>(smem + L.srcw);
+  float2 *scw = reinterpret_cast<float2 *>(smem + L.scw);
   int32_t *wbuf = reinterpret_cast<int32_t *>(smem + L.wbuf);
   int32_t *icnt = reinterpret_cast<int32_t *>(smem + L.icnt);
   int32_t *iblk = reinterpret_cast<int32_t *>(smem + L.iblk);
-  int32_t *fifo = reinterpret_cast<int32_t *>(smem + L.fifo);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NE; ++i) {
-      mbar_init(s_base + L.full + i * 8, 1);
+      mbar_init(s_base + L.ready + i * 8, 1);
+      mbar_init(s_base + L.data + i * 8, 1);
       mbar_init(s_base + L.empty + i * 8, 1);
     }
     for (int i = 0; i < kIS; ++i) icnt[i] = 0;
@@ -193,26 +211,16 @@ __global__ void __launch_bounds__(512, 1) ring_kernel(const __grid_constant__ Ri
   __syncthreads();
 
   if (warp == 0) {
-    // =========================================== producer ===========================================
+    // ====================== control warp: tickets, dependencies, chunk descriptors ======================
     const int total = ra.nitem * ra.nslab;
-    const uint64_t pol_in[2] = {make_policy(ra.pol_x), make_policy(ra.pol_xe_r)};
-    int my_q = 0;                 // lane g: chunks handed to consumer g so far
-    uint64_t busy = 0;            // queue entries holding an unconsumed chunk
-    int ring_head = 0, ring_free = ra.rs;
-    int fifo_head = 0, fifo_tail = 0;
-    int cur = 0;                  // consumer of the next chunk
+    int my_q = 0;                 // lane g: chunks handed to worker g so far
+    int cur = 0;                  // worker of the next chunk
     int item_seq = 0;
-    int wm[2] = {0, 0}, wm_slab = -1;   // completion watermarks: A blocks (for B items), B blocks (for discards)
+    int wm0 = 0, wm1 = 0, wm_slab = -1;   // completion watermarks: A blocks (for B items), B blocks (for discards)
     bool gave_up = false;
+    Prof prof;
+    prof.on = ra.prof != 0;
 
-    auto reclaim = [&]() {        // the oldest chunk in flight: wait until it is consumed, take its slots back
-      const int f = fifo[fifo_tail % NE];
-      const int id = f & 0xff, par = (f >> 8) & 1, rows = f >> 16;
-      mbar_wait(s_base + L.empty + id * 8, par);
-      busy &= ~(1ull << id);
-      ring_free += rows;
-      ++fifo_tail;
-    };
     auto claim = [&]() -> int {   // result valid in lane 0 only (broadcast where it is used)
       int t = 0;
       if (lane == 0) t = atomicAdd(ra.ctrl, 1);
@@ -242,12 +250,11 @@ __global__ void __launch_bounds__(512, 1) ring_kernel(const __grid_constant__ Ri
     };
     // all blocks [0, need) of one kind complete?  (relaxed polls, one acquire fence at the end)
     auto wait_blocks = [&](int kind, int slab, int need) {
-      if (slab != wm_slab) { wm_slab = slab; wm[0] = wm[1] = 0; }
-      int &w = wm[kind];
+      if (slab != wm_slab) { wm_slab = slab; wm0 = wm1 = 0; }
+      int w = kind == 0 ? wm0 : wm1;
       if (w >= need) return;
-      const int nblk = kind == 0 ? ra.nblkA : ra.nblkB, G = kind == 0 ? ra.GA : ra.GB;
+      const int G = kind == 0 ? ra.GA : ra.GB;
       const int *cnt = ra.ctrl + kCtrlHdr + (int64_t)slab * (ra.nblkA + ra.nblkB) + (kind == 0 ? 0 : ra.nblkA);
-      (void)nblk;
       unsigned spins = 0;
       while (w < need && !gave_up) {
         const int b = w + lane;
@@ -265,8 +272,8 @@ __global__ void __launch_bounds__(512, 1) ring_kernel(const __grid_constant__ Ri
           }
         }
       }
+      if (kind == 0) wm0 = w; else wm1 = w;
       asm volatile("fence.acquire.gpu;" ::: "memory");
-      asm volatile("fence.proxy.async.global;" ::: "memory");
     };
 
     auto process_item = [&](const int4 &it, int slab, int buf) {
@@ -288,6 +295,7 @@ __global__ void __launch_bounds__(512, 1) ring_kernel(const __grid_constant__ Ri
         return;
       }
       const int stage = kind;
+      const long long tw = prof.now();
       if (stage == 1 && it.w > 0) wait_blocks(0, slab, it.w);
       // completion slot
       int islot = -1;
@@ -297,12 +305,9 @@ __global__ void __launch_bounds__(512, 1) ring_kernel(const __grid_constant__ Ri
         while (lds_volatile(icnt + islot) != 0) {}
         if (lane == 0) sts_volatile(iblk + islot, blk_base + (stage == 0 ? 0 : ra.nblkA) + idx / kBlk);
       }
+      prof.add(2, tw);
       const int32_t *gsrc = ra.src[stage], *gdst = ra.dst[stage];
       const int32_t *wsrc = wbuf + buf * 2 * kMaxP, *wdst = wsrc + kMaxP;
-      const char *in_base = reinterpret_cast<const char *>(ra.in[stage] + col0);
-      const uint64_t row_stride = (uint64_t)ra.F * 4u;
-      const uint32_t row_bytes = (uint32_t)Fs * 4u;
-      const uint64_t pol = pol_in[stage];
       int nchunks = 0;
       for (int pos = it.x; pos < it.y; pos += 32) {
         const int rel = pos - it.x + lane;
@@ -315,50 +320,33 @@ __global__ void __launch_bounds__(512, 1) ring_kernel(const __grid_constant__ Ri
         const uint32_t endm = __ballot_sync(kFull, (dw & kEnd) != 0);
         int o = 0;
         while (o < nb) {
-          const int lim = min(ra.ch, nb - o);
+          const int lim = min(CH, nb - o);
           const uint32_t m = (endm >> o) & (lim >= 32 ? 0xffffffffu : ((1u << lim) - 1u));
           const int n = m ? 32 - __clz(m) : lim;              // up to the last unit end inside the limit
           const bool ends = ((m >> (n - 1)) & 1u) != 0;
-          // ---- hand rows [pos + o, pos + o + n) to consumer `cur`
+          // ---- hand rows [pos + o, pos + o + n) to worker `cur`
           const int q = __shfl_sync(kFull, my_q, cur);
-          const int e = q % QD, id = cur * QD + e, par = (q / QD) & 1;
-          while ((busy >> id) & 1ull) reclaim();
-          while (ring_free < n) reclaim();
+          const int id = cur * QD + q % QD;
+          if (q >= QD) {   // its previous use is consumed
+            const long long t0 = prof.now();
+            mbar_wait(s_base + L.empty + id * 8, (uint32_t)(q / QD - 1) & 1u);
+            prof.add(1, t0);
+          }
           if (lane == 0) {
             int i0 = 0, i1 = 0;
             if (stage == 1 && ra.niso > 0) {
               i0 = (int)((int64_t)ra.niso * (pos + o) / ra.npos);
               i1 = (int)((int64_t)ra.niso * (pos + o + n) / ra.npos);
             }
-            hdr[id * 2] = make_int4(n, ring_head, stage | ((islot + 1) << 1), col0);
+            hdr[id * 2] = make_int4(n, 0, stage | ((islot + 1) << 1), col0);
             hdr[id * 2 + 1] = make_int4(i0, i1, Fs, 0);
-            fifo[fifo_head % NE] = id | (par << 8) | (n << 16);
           }
           if (lane >= o && lane < o + n) {
-            dstw[id * 32 + lane - o] = (int32_t)dw;
-            srcw[id * 32 + lane - o] = (int32_t)sw;
+            dstw[id * CH + lane - o] = (int32_t)dw;
+            srcw[id * CH + lane - o] = (int32_t)sw;
           }
           __syncwarp();
-          if (elect_one()) {
-            const uint32_t bar = s_base + L.full + id * 8;
-            mbar_expect_tx(bar, (uint32_t)n * row_bytes);
-            int slot = ring_head;
-            uint32_t dsta = s_base + L.ring + (uint32_t)slot * slot_bytes;
-            const int32_t *rw = srcw + id * 32;
-#pragma unroll 4
-            for (int j = 0; j < n; ++j) {
-              const uint32_t r = (uint32_t)rw[j];
-              bulk_row(dsta, in_base + (uint64_t)r * row_stride, row_bytes, bar, pol);
-              ++slot; dsta += slot_bytes;
-              if (slot == ra.rs) { slot = 0; dsta = s_base + L.ring; }
-            }
-          }
-          __syncwarp();
-          ++fifo_head;
-          busy |= 1ull << id;
-          ring_free -= n;
-          ring_head += n;
-          if (ring_head >= ra.rs) ring_head -= ra.rs;
+          if (lane == 0) mbar_arrive(s_base + L.ready + id * 8);
           if (lane == cur) ++my_q;
           ++nchunks;
           if (ends) cur = cur + 1 == NC ? 0 : cur + 1;
@@ -374,7 +362,7 @@ __global__ void __launch_bounds__(512, 1) ring_kernel(const __grid_constant__ Ri
       }
     };
 
-    // ---- ticket pipeline: ticket (i + 3) claimed, item (i + 2) loading, words (i + 1) in flight, item i issued
+    // ---- ticket pipeline: ticket (i + 3) claimed, item (i + 2) loading, words (i + 1) in flight, item i cut
     int tC = claim();
     int4 i0, i1;
     int s0, s1;
@@ -392,7 +380,9 @@ __global__ void __launch_bounds__(512, 1) ring_kernel(const __grid_constant__ Ri
       tC = claim();
       asm volatile("cp.async.wait_group 1;" ::: "memory");
       __syncwarp();
+      const long long tp = prof.now();
       process_item(i0, s0, nproc & 1);
+      prof.add(0, tp);
       __syncwarp();
       i0 = i1; s0 = s1; i1 = i2; s1 = s2;
       ++nproc;
@@ -402,54 +392,137 @@ __global__ void __launch_bounds__(512, 1) ring_kernel(const __grid_constant__ Ri
     for (int g = 0; g < NC; ++g) {
       const int q = __shfl_sync(kFull, my_q, g);
       const int id = g * QD + q % QD;
-      while ((busy >> id) & 1ull) reclaim();
+      if (q >= QD) mbar_wait(s_base + L.empty + id * 8, (uint32_t)(q / QD - 1) & 1u);
       if (lane == 0) {
         hdr[id * 2] = make_int4(kStop, 0, 0, 0);
-        mbar_arrive(s_base + L.full + id * 8);
+        mbar_arrive(s_base + L.ready + id * 8);
       }
       __syncwarp();
     }
+    prof.flush(ra.ctrl, 2, lane);
   } else {
-    // =========================================== consumer ===========================================
+    // ====================== worker warp: issues its chunks' row copies, sums them, stores ======================
     const int g = warp - 1;
-    const uint64_t pol_out[2] = {make_policy(ra.pol_xe_w), make_policy(ra.pol_y)};
+    const uint64_t pol_x = make_policy(ra.pol_x), pol_xe_r = make_policy(ra.pol_xe_r);
+    const uint64_t pol_xe_w = make_policy(ra.pol_xe_w), pol_y = make_policy(ra.pol_y);
+    const uint32_t ring_a = s_base + L.ring + (uint32_t)g * rsw * slot_bytes;
+    const unsigned char *ring_p = smem + L.ring + (size_t)g * rsw * slot_bytes + lane * 16;
+    const uint64_t row_stride = (uint64_t)ra.F * 4u;
     float4 acc[VPL];
 #pragma unroll
     for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
     constexpr int RB = VPL == 4 ? 2 : 4;   // rows read from shared memory per batch
-    for (int k = 0;; ++k) {
-      const int id = g * QD + k % QD;
-      mbar_wait(s_base + L.full + id * 8, (uint32_t)(k / QD) & 1u);
-      const int4 h0 = hdr[id * 2], h1 = hdr[id * 2 + 1];
-      const int n = h0.x;
-      if (n == kStop) break;
-      const int slot0 = h0.y, stage = h0.z & 1, islot = (h0.z >> 1) - 1, col0 = h0.w, Fs = h1.z;
-      uint32_t dw = 0;
-      float wv = 1.0f, sc = 1.0f;
-      if (lane < n) {
-        dw = (uint32_t)dstw[id * 32 + lane];
-        if (HAS_WIN && stage == 0) wv = __ldg(ra.w_in + (uint32_t)srcw[id * 32 + lane]);
-        if (dw & kEnd) {
-          const uint32_t orow = dw & kRowMask;
-          const float *o1 = ra.w_o1[stage], *o2 = ra.w_o2[stage];
-          if (o1) sc = __ldg(o1 + orow);
-          if (o2) sc *= __ldg(o2 + orow);
-        }
+    int issued = 0, done = 0;              // chunks whose copies are issued / that are consumed
+    int ring_head = 0, ring_used = 0;
+    bool stopped = false;
+    int pend_id = -1;                      // chunk whose scales are still in registers
+    float pend_sc = 1.0f, pend_w = 1.0f;
+    Prof prof;
+    prof.on = ra.prof != 0;
+    auto flush_pending = [&]() {
+      if (pend_id >= 0) {
+        if (lane < CH) scw[pend_id * CH + lane] = make_float2(pend_sc, pend_w);
+        pend_id = -1;
       }
+    };
+    for (;;) {
+      // ---- issue: every chunk whose descriptor is there and whose rows fit the ring
+      while (!stopped && issued - done < QD) {
+        const int id = g * QD + issued % QD;
+        const uint32_t rbar = s_base + L.ready + id * 8, par = (uint32_t)(issued / QD) & 1u;
+        if (issued == done) {                              // nothing in flight: sleep until there is work
+          const long long t0 = prof.now();
+          mbar_wait(rbar, par);
+          prof.add(2, t0);
+        } else {
+          uint32_t ok;
+          asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                       : "=r"(ok) : "r"(rbar), "r"(par) : "memory");
+          if (!ok) break;
+        }
+        const int4 h0 = hdr[id * 2];
+        const int n = h0.x;
+        if (n == kStop) { stopped = true; break; }
+        if (ring_used + n > rsw) break;
+        const int stage = h0.z & 1, col0 = h0.w;
+        const int Fs = hdr[id * 2 + 1].z;
+        flush_pending();
+        if (lane == 0) hdr[id * 2].y = ring_head;
+        const long long ti = prof.now();
+        if (elect_one()) {
+          const uint32_t bar = s_base + L.data + id * 8;
+          const uint32_t row_bytes = (uint32_t)Fs * 4u;
+          mbar_expect_tx(bar, (uint32_t)n * row_bytes);
+          // stage B reads rows that generic-proxy stores of this launch produced (ordered by the control
+          // warp's acquire and the descriptor barrier): make them visible to the async proxy
+          if (stage) asm volatile("fence.proxy.async.global;" ::: "memory");
+          const char *in_base = reinterpret_cast<const char *>(ra.in[stage] + col0);
+          const uint64_t pol = stage ? pol_xe_r : pol_x;
+          int slot = ring_head;
+          uint32_t dsta = ring_a + (uint32_t)slot * slot_bytes;
+          const int32_t *rw = srcw + id * CH;
+#pragma unroll 4
+          for (int j = 0; j < n; ++j) {
+            const uint32_t r = (uint32_t)rw[j];
+            bulk_row(dsta, in_base + (uint64_t)r * row_stride, row_bytes, bar, pol);
+            ++slot; dsta += slot_bytes;
+            if (slot == rsw) { slot = 0; dsta = ring_a; }
+          }
+        }
+        __syncwarp();
+        prof.add(0, ti);
+        // the chunk's scales: loaded now, parked in shared memory when the next chunk is issued / consumed
+        pend_id = id; pend_sc = 1.0f; pend_w = 1.0f;
+        if (lane < n) {
+          const uint32_t dw = (uint32_t)dstw[id * CH + lane];
+          if (HAS_WIN && stage == 0) pend_w = __ldg(ra.w_in + (uint32_t)srcw[id * CH + lane]);
+          if (dw & kEnd) {
+            const uint32_t orow = dw & kRowMask;
+            const float *o1 = stage ? ra.w_o1[1] : ra.w_o1[0], *o2 = stage ? ra.w_o2[1] : ra.w_o2[0];
+            if (o1) pend_sc = __ldg(o1 + orow);
+            if (o2) pend_sc *= __ldg(o2 + orow);
+          }
+        }
+        ring_head += n;
+        if (ring_head >= rsw) ring_head -= rsw;
+        ring_used += n;
+        ++issued;
+      }
+      if (issued == done) {
+        if (stopped) break;
+        continue;
+      }
+      // ---- consume the oldest chunk in flight
+      flush_pending();
+      __syncwarp();
+      const int id = g * QD + done % QD;
+      {
+        const long long t0 = prof.now();
+        mbar_wait(s_base + L.data + id * 8, (uint32_t)(done / QD) & 1u);
+        prof.add(1, t0);
+      }
+      const int4 h0 = hdr[id * 2], h1 = hdr[id * 2 + 1];
+      const int n = h0.x, slot0 = h0.y, stage = h0.z & 1, islot = (h0.z >> 1) - 1, col0 = h0.w, Fs = h1.z;
+      uint32_t dw = 0;
+      float2 sw2 = make_float2(1.0f, 1.0f);
+      if (lane < n) {
+        dw = (uint32_t)dstw[id * CH + lane];
+        sw2 = scw[id * CH + lane];
+      }
+      const float sc = sw2.x, wv = sw2.y;
       const uint32_t endm = __ballot_sync(kFull, (dw & kEnd) != 0);
       bool ok[VPL];
 #pragma unroll
       for (int v = 0; v < VPL; ++v) ok[v] = (lane + 32 * v) * 4 < Fs;
-      float *out = ra.out[stage] + col0 + lane * 4;
-      const uint64_t pol = pol_out[stage];
-      const unsigned char *ring = smem + L.ring + lane * 16;
+      float *out = (stage ? ra.out[1] : ra.out[0]) + col0 + lane * 4;
+      const uint64_t pol = stage ? pol_y : pol_xe_w;
       for (int j0 = 0; j0 < n; j0 += RB) {
         float4 x[RB][VPL];
 #pragma unroll
         for (int u = 0; u < RB; ++u) {
           int slot = slot0 + min(j0 + u, n - 1);
-          if (slot >= ra.rs) slot -= ra.rs;
-          const unsigned char *rp = ring + (uint32_t)slot * slot_bytes;
+          if (slot >= rsw) slot -= rsw;
+          const unsigned char *rp = ring_p + (uint32_t)slot * slot_bytes;
 #pragma unroll
           for (int v = 0; v < VPL; ++v)
             x[u][v] = ok[v] ? *reinterpret_cast<const float4 *>(rp + v * 512) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -498,14 +571,17 @@ __global__ void __launch_bounds__(512, 1) ring_kernel(const __grid_constant__ Ri
         float *yp = ra.out[1] + (int64_t)__ldg(ra.iso + i) * ra.F + col0 + lane * 4;
 #pragma unroll
         for (int v = 0; v < VPL; ++v)
-          if (ok[v]) st_row_hint(yp + v * 128, make_float4(0.f, 0.f, 0.f, 0.f), pol_out[1]);
+          if (ok[v]) st_row_hint(yp + v * 128, make_float4(0.f, 0.f, 0.f, 0.f), pol_y);
       }
+      ring_used -= n;
+      ++done;
       __syncwarp();
       if (lane == 0) {
         if (islot >= 0 && atom_add_cta(icnt + islot, 1) + 1 == kBig) complete_item(ra, icnt, iblk, islot);
         mbar_arrive(s_base + L.empty + id * 8);
       }
     }
+    prof.flush(ra.ctrl, 5, lane);
   }
 }
 
@@ -727,22 +803,24 @@ int launch_ring(hgPlan *p, const dev::Args &a, cudaStream_t s) {
   const int nslab = (F + slabF - 1) / slabF;
   const int vpl = slabF <= 128 ? 1 : (slabF <= 256 ? 2 : 4);
   const int slot_bytes = slabF * 4;
-  int nc = tune_get("ring_consumers", 7);
-  if (nc < 1) nc = 1;
-  if (nc > 15) nc = 15;
+  int nc = tune_get("ring_workers", 0);
+  if (nc <= 0) nc = slot_bytes >= 2048 ? 4 : 8;
+  if (nc > 16) nc = 16;
   int ctas = tune_get("ring_ctas", 2);
   if (ctas < 1) ctas = 1;
   int qd = tune_get("ring_qd", 0);
-  if (qd <= 0) qd = kMaxEntries / nc > 8 ? 8 : kMaxEntries / nc;
-  if (nc * qd > kMaxEntries) qd = kMaxEntries / nc;
+  if (qd <= 0) qd = kMaxEntries / nc > 6 ? 6 : kMaxEntries / nc;
+  if (qd < 2) qd = 2;
+  if (nc * qd > kMaxEntries) nc = kMaxEntries / qd;
+  int ring_kb = tune_get("ring_kb", 0);          // per CTA, shared out among the workers
+  if (ring_kb <= 0) ring_kb = ctas >= 2 ? 80 : 176;
+  int rsw = ring_kb * 1024 / slot_bytes / nc;    // ring slots of one worker
+  if (rsw < 2) rsw = 2;
   int ch = tune_get("ring_chunk", 0);
   if (ch <= 0) ch = 8192 / slot_bytes;
-  if (ch < 2) ch = 2;
+  if (ch > rsw / 2) ch = rsw / 2;
+  if (ch < 1) ch = 1;
   if (ch > 32) ch = 32;
-  int ring_kb = tune_get("ring_kb", 0);
-  if (ring_kb <= 0) ring_kb = ctas >= 2 ? 80 : 176;
-  int rs = ring_kb * 1024 / slot_bytes;
-  if (rs < 2 * ch) rs = 2 * ch;
   int item_kb = tune_get("ring_item_kb", 32);
   int bpi = item_kb * 1024 / (kL0 * slot_bytes);
   if (bpi < 1) bpi = 1;
@@ -773,12 +851,13 @@ int launch_ring(hgPlan *p, const dev::Args &a, cudaStream_t s) {
   ra.nitem = sc->nitem; ra.nslab = nslab; ra.slabF = slabF; ra.F = F;
   ra.nblkA = sc->nblkA; ra.nblkB = sc->nblkB; ra.GA = sc->GA; ra.GB = sc->GB;
   ra.npos = (int32_t)p->nnz;
-  ra.rs = rs; ra.ch = ch; ra.qd = qd; ra.track_b = discard;
+  ra.rs = rsw; ra.ch = ch; ra.qd = qd; ra.track_b = discard;
   ra.pol_x = tune_get("ring_pol_x", kPolFirst);
   ra.pol_xe_w = tune_get("ring_pol_xe_w", kPolLast);
   ra.pol_xe_r = tune_get("ring_pol_xe_r", kPolNormal);
   ra.pol_y = tune_get("ring_pol_y", kPolFirst);
-  const Layout L = make_layout(rs, slot_bytes, nc * qd);
+  ra.prof = tune_get("ring_prof", 0);
+  const Layout L = make_layout(nc, rsw, slot_bytes, nc * qd, ch);
   const unsigned threads = 32u * (1 + nc);
   p->rg_last_ctrl = sc->ctrl;
   ++p->kernels_launched;
@@ -786,6 +865,14 @@ int launch_ring(hgPlan *p, const dev::Args &a, cudaStream_t s) {
   if (vpl == 1) return launch_vpl<1>(ra, has_win, grid, threads, L.total, s);
   if (vpl == 2) return launch_vpl<2>(ra, has_win, grid, threads, L.total, s);
   return launch_vpl<4>(ra, has_win, grid, threads, L.total, s);
+}
+
+int ring_debug(hgPlan *plan, int32_t *out8, cudaStream_t s) {
+  for (int i = 0; i < 8; ++i) out8[i] = 0;
+  if (!plan->rg_last_ctrl) return HG_OK;
+  HG_CUDA_TRY(cudaMemcpyAsync(out8, plan->rg_last_ctrl, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  HG_CUDA_TRY(cudaStreamSynchronize(s));
+  return HG_OK;
 }
 
 int ring_check(hgPlan *plan, cudaStream_t s) {

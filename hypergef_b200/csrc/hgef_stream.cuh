@@ -23,5 +23,6 @@ bool ring_available(const hgPlan *plan, int F, bool force);
 int launch_ring(hgPlan *plan, const dev::Args &a, cudaStream_t s);
 void ring_free(hgPlan *plan);
 int ring_check(hgPlan *plan, cudaStream_t s);
+int ring_debug(hgPlan *plan, int32_t *out8, cudaStream_t s);
 
 }  // namespace hg

@@ -141,6 +141,12 @@ class Plan:
         _native.call("hg_plan_launches", self.handle, C.byref(n))
         return n.value
 
+    def debug_words(self):
+        """The 8 control words of the last ring-form launch (hg_plan_debug; diagnostic)."""
+        out = (C.c_int32 * 8)()
+        _native.call("hg_plan_debug", self.handle, out, torch.cuda.current_stream(self.device_index).cuda_stream)
+        return list(out)
+
     def check(self) -> None:
         """Synchronise and raise if any launch issued with this plan faulted (hg_plan_check)."""
         _native.call("hg_plan_check", self.handle, torch.cuda.current_stream(self.device_index).cuda_stream)

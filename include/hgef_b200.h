@@ -127,6 +127,10 @@ HG_API int hg_plan_info(const hgPlan *plan, int64_t *nseg, int64_t *nheavy_edges
 /* Number of this library's kernels launched through the plan so far (aggregation calls only). */
 HG_API int hg_plan_launches(const hgPlan *plan, int64_t *kernels);
 
+/* Diagnostic: the 8 control words of the last ring-form launch (ticket counter, give-up flag and, with the
+ * tuning knob ring_prof = 1, a clock breakdown of the control and worker warps in kilo-clocks). */
+HG_API int hg_plan_debug(hgPlan *plan, int32_t *h_out8, void *stream);
+
 /* Synchronises `stream` and reports (HG_ECUDA) any fault of the launches issued with this plan,
  * including the fused kernel's bounded-wait give-up.  The reference has no equivalent: it never
  * checks a launch (hgnnaggr_cuda.cu:383-404). */

@@ -323,7 +323,7 @@ def test_stream_form_configurations(shape, replicas, cuda_device, monkeypatch):
             assert orc.rel_err(_np(out), want) < TOL
 
 
-RING_KNOBS = ("ring_consumers", "ring_ctas", "ring_qd", "ring_chunk", "ring_kb", "ring_item_kb", "ring_lag_b", "ring_lag_c",
+RING_KNOBS = ("ring_workers", "ring_ctas", "ring_qd", "ring_chunk", "ring_kb", "ring_item_kb", "ring_lag_b", "ring_lag_c",
               "ring_discard", "ring_pol_x", "ring_pol_xe_w", "ring_pol_xe_r", "ring_pol_y")
 
 
@@ -339,12 +339,12 @@ def test_ring_form_configurations(shape, replicas, cuda_device):
     plan = ops.get_plan(hg.group_key, hg.group_row, hg.group_start, hg.group_end, hg.H_T_colind, N, M)
     W = torch.rand(M, device=cuda_device) + 0.5
     ptr, ind = _np(hg.H_T_csrptr), _np(hg.H_T_colind)
-    combos = [dict(), dict(ring_lag_b=0, ring_lag_c=0), dict(ring_consumers=3, ring_ctas=1, ring_kb=160),
-              dict(ring_consumers=15, ring_qd=2, ring_chunk=2, ring_item_kb=8),
+    combos = [dict(), dict(ring_lag_b=0, ring_lag_c=0), dict(ring_workers=3, ring_ctas=1, ring_kb=160),
+              dict(ring_workers=16, ring_qd=2, ring_chunk=2, ring_item_kb=8),
               dict(ring_chunk=32, ring_item_kb=256, ring_kb=64), dict(ring_discard=0, ring_lag_b=1000000),
               dict(ring_kb=16, ring_item_kb=4, ring_lag_b=3, ring_lag_c=1),
               dict(ring_pol_x=0, ring_pol_xe_w=0, ring_pol_xe_r=1, ring_pol_y=0, ring_ctas=3, ring_kb=48),
-              dict(ring_consumers=1, ring_qd=1, ring_chunk=5, ring_ctas=4, ring_kb=32)]
+              dict(ring_workers=1, ring_qd=2, ring_chunk=5, ring_ctas=4, ring_kb=32)]
     try:
         for F in (4, 20, 32, 64, 100, 128, 256, 384, 512, 640, 1056):
             X = torch.randn(N, F, device=cuda_device)

@@ -52,6 +52,9 @@ for cfg in (args.sweep.split(";") if args.sweep else [""]):
         b.record(); torch.cuda.synchronize(); plan.check()
         us = a.elapsed_time(b) / args.iters * 1e3
         balg = 8 * F * N + 4 * Z + 12 * M + 4 * N + 4
+        if "ring_prof" in TUNED:
+            w = plan.debug_words()
+            out.append(f"[prof, kclk summed over warps, last launch: control items {w[2]} of which wait-empty {w[3]} wait-deps {w[4]} | worker issue {w[5]} wait-data {w[6]} idle {w[7]}]")
         out.append(f"F={F}: {us:8.1f} us {balg / us / 1e3:7.1f} GB/s ({balg / us / 1e3 / 6536 * 100:4.1f}%)")
         del X, Y
     print(f"[{args.tag} {cfg} {args.shape}x{args.replicas} N={N} Z={Z} heavy={plan.nheavy_edges}] " + " | ".join(out), flush=True)

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("HGEF_B200_LIB") or os.path.join(_HERE, "libhgef_b200.
 
 HG_OK, HG_EINVAL, HG_ECUDA, HG_ENOMEM, HG_EEMPTY, HG_EGRAPH = range(6)
 HG_ACCUMULATE, HG_FORCE_SCALAR, HG_TWO_PASS, HG_FORCE_FUSED, HG_FORCE_PULL, HG_FORCE_STREAM = 1, 4, 8, 16, 32, 64
-HG_FORCE_RING = 128
+HG_FORCE_RING, HG_FORCE_FSTREAM = 128, 256
 
 
 class HgefBuildError(ImportError):

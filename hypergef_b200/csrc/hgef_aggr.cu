@@ -243,8 +243,17 @@ int hg_aggr_forward(hgPlan *plan, const float *d_X, const float *d_s1, const flo
   cudaStream_t s = (cudaStream_t)stream;
   const bool vec4 = F % 4 == 0 && !(flags & HG_FORCE_SCALAR) && aligned16(d_X) && aligned16(d_Y);
   const bool vec = vec4 && F <= 512;
-  // ring form: one persistent launch, TMA row ring, hyperedge features through the L2 (hgef_ring.cu)
-  const bool use_ring = vec4 && !(flags & (HG_ACCUMULATE | HG_TWO_PASS | HG_FORCE_FUSED | HG_FORCE_PULL | HG_FORCE_STREAM)) &&
+  // fused stream form: one persistent launch of register-only row streams, hyperedge features handed over
+  // through the L2 and discarded there (hgef_fstream.cu): the default when Y exceeds the L2
+  const bool use_fstream = vec4 && !(flags & (HG_ACCUMULATE | HG_TWO_PASS | HG_FORCE_FUSED | HG_FORCE_PULL | HG_FORCE_STREAM | HG_FORCE_RING)) &&
+                           fstream_available(plan, F, (flags & HG_FORCE_FSTREAM) != 0);
+  if (use_fstream) {
+    Args pa{};
+    pa.X = d_X; pa.s1 = d_s1; pa.s2 = d_s2; pa.a_out = d_a_out; pa.a_in = d_a_in; pa.Y = d_Y; pa.F = F;
+    return launch_fstream(plan, pa, s);
+  }
+  // ring form: the same schedule with TMA bulk row copies into a shared-memory ring (hgef_ring.cu)
+  const bool use_ring = vec4 && !(flags & (HG_ACCUMULATE | HG_TWO_PASS | HG_FORCE_FUSED | HG_FORCE_PULL | HG_FORCE_STREAM | HG_FORCE_FSTREAM)) &&
                         ring_available(plan, F, (flags & HG_FORCE_RING) != 0);
   if (use_ring) {
     Args pa{};
@@ -252,7 +261,7 @@ int hg_aggr_forward(hgPlan *plan, const float *d_X, const float *d_s1, const flo
     return launch_ring(plan, pa, s);
   }
   // stream form: both stages as lean register-only row streams, two launches (hgef_stream.cu)
-  const bool use_stream = vec4 && !(flags & (HG_ACCUMULATE | HG_TWO_PASS | HG_FORCE_FUSED | HG_FORCE_PULL | HG_FORCE_RING)) &&
+  const bool use_stream = vec4 && !(flags & (HG_ACCUMULATE | HG_TWO_PASS | HG_FORCE_FUSED | HG_FORCE_PULL | HG_FORCE_RING | HG_FORCE_FSTREAM)) &&
                       stream_available(plan, F, (flags & HG_FORCE_STREAM) != 0);
   if (use_stream) {
     Args pa{};

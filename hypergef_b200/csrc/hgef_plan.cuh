@@ -32,6 +32,7 @@ struct hgPlan {
   // stream form (hgef_stream.cu): row programs of the two stages, base runs, stage-B vertex order
   int32_t *st_srcA = nullptr, *st_dstA = nullptr, *st_runA = nullptr;
   int32_t *st_srcB = nullptr, *st_dstB = nullptr, *st_needB = nullptr, *st_runB = nullptr;
+  int32_t *st_ptrB = nullptr;     // [N + 1] first stage-B position of every unit (vertex in st_perm order)
   int32_t *st_perm = nullptr;     // [N] vertices ordered by their last hyperedge; the tail holds the isolated ones
   int32_t *st_ctrl = nullptr;     // ticket counters of the two-launch form
   int32_t *st_last_ctrl = nullptr;
@@ -49,11 +50,14 @@ struct hgPlan {
   // ring form (hgef_ring.cu): hyperedges ordered by their last stage-B read position (the discard order), and
   // merged A / B / discard ticket orders for one item size and pair of lags
   int32_t *rg_dperm = nullptr, *rg_dlast = nullptr;
+  int32_t *rg_runA = nullptr, *rg_runB = nullptr;   // unit-aligned runs of kL0f positions
+  int64_t rg_nrunA = 0, rg_nrunB = 0;
   int32_t rg_ready = 0;
   struct RingSched {
-    int bpi, lagB, lagC, nslab, discard;
+    int bpi, lagB, lagC, nslab, discard, ksub;
     int32_t GA, GB, GC, nblkA, nblkB, nitem;
-    int4 *items;                  // per ticket: {first position, end position, kind | index << 2, blocks needed}
+    int4 *items;                  // per ticket two words: {first position, end position, kind | index << 2, blocks needed},
+                                  //   {sub-stream split points 1..3, 0}
     int32_t *ctrl;                // kCtrlHdr + nslab * (nblkA + nblkB) words
   };
   RingSched rg_sched[kMaxSched];

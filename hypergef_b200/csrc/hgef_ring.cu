@@ -46,7 +46,6 @@ constexpr int kIS = 8;            // items whose completion a CTA tracks at one 
 constexpr int kBig = 1 << 20;
 constexpr int kMaxEntries = 96;   // descriptor-queue entries per CTA (workers x depth)
 constexpr int kStop = -1;
-enum { kKindA = 0, kKindB = 1, kKindC = 2 };
 enum { kPolNormal = 0, kPolFirst = 1, kPolLast = 2 };
 
 struct RingArgs {
@@ -144,7 +143,7 @@ struct Prof {   // diagnostic clock breakdown of one warp
   __device__ __forceinline__ void add(int i, long long t0) { if (on) t[i] += clock64() - t0; }
   __device__ __forceinline__ void flush(int *ctrl, int base, int lane) {
     if (on && lane == 0)
-      for (int i = 0; i < 3; ++i) atomicAdd(ctrl + base + i, (int)(t[i] >> 10));
+      for (int i = 0; i < 3; ++i) atomicAdd(ctrl + kDbgOff + base + i, (int)(t[i] >> 10));
   }
 };
 
@@ -176,7 +175,7 @@ __device__ __forceinline__ void complete_item(const RingArgs &ra, int *icnt, con
   const int b = lds_volatile(iblk + islot);
   asm volatile("fence.proxy.async.global;" ::: "memory");
   asm volatile("fence.release.gpu;" ::: "memory");
-  red_inc_relaxed(ra.ctrl + kCtrlHdr + b);
+  red_inc_relaxed(ra.ctrl + kCntOff + b);
   sts_volatile(icnt + islot, 0);
 }
 
@@ -232,7 +231,7 @@ __global__ void __launch_bounds__(544, 1) ring_kernel(const __grid_constant__ Ri
       slab = -1;
       if (t < total) {
         slab = ra.nslab > 1 ? t / ra.nitem : 0;
-        it = __ldg(ra.items + (t - slab * ra.nitem));
+        it = __ldg(ra.items + 2 * (t - slab * ra.nitem));
       }
     };
     auto prefetch_words = [&](const int4 &it, int slab, int buf) {
@@ -254,7 +253,7 @@ __global__ void __launch_bounds__(544, 1) ring_kernel(const __grid_constant__ Ri
       int w = kind == 0 ? wm0 : wm1;
       if (w >= need) return;
       const int G = kind == 0 ? ra.GA : ra.GB;
-      const int *cnt = ra.ctrl + kCtrlHdr + (int64_t)slab * (ra.nblkA + ra.nblkB) + (kind == 0 ? 0 : ra.nblkA);
+      const int *cnt = ra.ctrl + kCntOff + (int64_t)slab * (ra.nblkA + ra.nblkB) + (kind == 0 ? 0 : ra.nblkA);
       unsigned spins = 0;
       while (w < need && !gave_up) {
         const int b = w + lane;
@@ -266,8 +265,8 @@ __global__ void __launch_bounds__(544, 1) ring_kernel(const __grid_constant__ Ri
           __nanosleep(100);
           ++spins;
           // bounded: a protocol bug must not hang the GPU; once one item gave up, nobody waits any more
-          if (spins > (1u << 20) || ((spins & 255u) == 0 && ld_relaxed(ra.ctrl + 1) != 0)) {
-            if (lane == 0) atomicExch(ra.ctrl + 1, 1);
+          if (spins > (1u << 20) || ((spins & 255u) == 0 && ld_relaxed(ra.ctrl + kFlagOff) != 0)) {
+            if (lane == 0) atomicExch(ra.ctrl + kFlagOff, 1);
             gave_up = true;
           }
         }
@@ -399,7 +398,7 @@ __global__ void __launch_bounds__(544, 1) ring_kernel(const __grid_constant__ Ri
       }
       __syncwarp();
     }
-    prof.flush(ra.ctrl, 2, lane);
+    prof.flush(ra.ctrl, 0, lane);
   } else {
     // ====================== worker warp: issues its chunks' row copies, sums them, stores ======================
     const int g = warp - 1;
@@ -581,7 +580,7 @@ __global__ void __launch_bounds__(544, 1) ring_kernel(const __grid_constant__ Ri
         mbar_arrive(s_base + L.empty + id * 8);
       }
     }
-    prof.flush(ra.ctrl, 5, lane);
+    prof.flush(ra.ctrl, 3, lane);
   }
 }
 
@@ -657,21 +656,25 @@ __global__ void sched_keys_kernel(int32_t GA, int32_t GB, int32_t GC, int32_t la
   }
 }
 
-__global__ void sched_items_kernel(int32_t n, const int32_t *__restrict__ vals, int32_t bpi, const int32_t *__restrict__ runA,
-                                   int32_t nrunA, const int32_t *__restrict__ runB, int32_t nrunB,
-                                   const int32_t *__restrict__ need_blk, const int32_t *__restrict__ dlast, int32_t M,
-                                   int32_t GC, int4 *__restrict__ items) {
+__global__ void sched_items_kernel(int32_t n, const int32_t *__restrict__ vals, int32_t bpi, int32_t ksub,
+                                   const int32_t *__restrict__ runA, int32_t nrunA, const int32_t *__restrict__ runB,
+                                   int32_t nrunB, const int32_t *__restrict__ need_blk, const int32_t *__restrict__ dlast,
+                                   int32_t M, int32_t GC, int4 *__restrict__ items) {
   const int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const int32_t v = vals[k], kind = v & 3, idx = v >> 2;
-  int4 it = make_int4(0, 0, v, 0);
-  if (kind == kKindA) {
-    it.x = runA[min((int64_t)idx * bpi, (int64_t)nrunA)];
-    it.y = runA[min(((int64_t)idx + 1) * bpi, (int64_t)nrunA)];
-  } else if (kind == kKindB) {
-    it.x = runB[min((int64_t)idx * bpi, (int64_t)nrunB)];
-    it.y = runB[min(((int64_t)idx + 1) * bpi, (int64_t)nrunB)];
-    it.w = need_blk[idx];
+  int4 it = make_int4(0, 0, v, 0), sp = make_int4(0, 0, 0, 0);
+  if (kind == kKindA || kind == kKindB) {
+    const int32_t *run = kind == kKindA ? runA : runB;
+    const int64_t nrun = kind == kKindA ? nrunA : nrunB;
+    auto at = [&](int64_t r) { return run[min(r, nrun)]; };
+    it.x = at((int64_t)idx * bpi);
+    it.y = at(((int64_t)idx + 1) * bpi);
+    const int32_t q = bpi / ksub;   // runs per sub-stream
+    sp.x = ksub > 1 ? at((int64_t)idx * bpi + q) : it.y;
+    sp.y = ksub > 2 ? at((int64_t)idx * bpi + 2 * q) : it.y;
+    sp.z = ksub > 3 ? at((int64_t)idx * bpi + 3 * q) : it.y;
+    if (kind == kKindB) it.w = need_blk[idx];
   } else {
     // hyperedges whose last reader lies in B block idx: dlast in [first position of the block, end of the block)
     const int32_t p0 = runB[min((int64_t)idx * kBlk * bpi, (int64_t)nrunB)];
@@ -688,7 +691,8 @@ __global__ void sched_items_kernel(int32_t n, const int32_t *__restrict__ vals, 
     it.y = lower(p1);
     it.w = idx + 1;
   }
-  items[k] = it;
+  items[2 * k] = it;
+  items[2 * k + 1] = sp;
 }
 
 int build_discard(hgPlan *p, cudaStream_t s) {
@@ -707,15 +711,22 @@ int build_discard(hgPlan *p, cudaStream_t s) {
   DevBuf<char> ws;
   HG_CUDA_TRY(ws.alloc(bytes));
   HG_CUDA_TRY(cub::DeviceRadixSort::SortPairs(ws.p, bytes, last.p, p->rg_dlast, ids.p, p->rg_dperm, M, 0, 32, s));
+  if (int rc = stream_build_runs(p, kL0f, &p->rg_runA, &p->rg_nrunA, &p->rg_runB, &p->rg_nrunB, s)) return rc;
   HG_CUDA_TRY(cudaStreamSynchronize(s));
   p->rg_ready = 1;
   return HG_OK;
 }
 
-int get_sched(hgPlan *p, int bpi, int lagB, int lagC, int nslab, int discard, cudaStream_t s, hgPlan::RingSched **out) {
+}  // namespace
+
+int fused_get_sched(hgPlan *p, int bpi, int lagB, int lagC, int nslab, int discard, int ksub, cudaStream_t s,
+                    hgPlan::RingSched **out) {
   for (int i = 0; i < p->rg_nsched; ++i) {
     hgPlan::RingSched &c = p->rg_sched[i];
-    if (c.bpi == bpi && c.lagB == lagB && c.lagC == lagC && c.discard == discard && c.nslab >= nslab) { *out = &c; return HG_OK; }
+    if (c.bpi == bpi && c.lagB == lagB && c.lagC == lagC && c.discard == discard && c.ksub == ksub && c.nslab >= nslab) {
+      *out = &c;
+      return HG_OK;
+    }
   }
   if (p->rg_nsched == hgPlan::kMaxSched) {   // recycle the oldest entry
     HG_CUDA_TRY(cudaStreamSynchronize(s));
@@ -725,22 +736,22 @@ int get_sched(hgPlan *p, int bpi, int lagB, int lagC, int nslab, int discard, cu
   }
   if (int rc = build_discard(p, s)) return rc;
   hgPlan::RingSched c{};
-  c.bpi = bpi; c.lagB = lagB; c.lagC = lagC; c.nslab = nslab; c.discard = discard;
-  c.GA = (int32_t)ceil_div<int64_t>(p->st_nrunA, bpi);
-  c.GB = (int32_t)ceil_div<int64_t>(p->st_nrunB, bpi);
+  c.bpi = bpi; c.lagB = lagB; c.lagC = lagC; c.nslab = nslab; c.discard = discard; c.ksub = ksub;
+  c.GA = (int32_t)ceil_div<int64_t>(p->rg_nrunA, bpi);
+  c.GB = (int32_t)ceil_div<int64_t>(p->rg_nrunB, bpi);
   c.nblkA = (c.GA + kBlk - 1) / kBlk;
   c.nblkB = (c.GB + kBlk - 1) / kBlk;
   c.GC = discard ? c.nblkB : 0;
   c.nitem = c.GA + c.GB + c.GC;
-  if (int rc = dev_alloc(&c.items, (size_t)c.nitem)) return rc;
-  if (int rc = dev_alloc(&c.ctrl, (size_t)kCtrlHdr + (size_t)(c.nblkA + c.nblkB) * nslab)) return rc;
+  if (int rc = dev_alloc(&c.items, (size_t)c.nitem * 2)) return rc;
+  if (int rc = dev_alloc(&c.ctrl, (size_t)kCntOff + (size_t)(c.nblkA + c.nblkB) * nslab)) return rc;
   DevBuf<int32_t> a_after, need_blk, vals, vals_s;
   DevBuf<uint64_t> keys, keys_s;
   HG_CUDA_TRY(a_after.alloc(c.GB)); HG_CUDA_TRY(need_blk.alloc(c.GB));
   HG_CUDA_TRY(vals.alloc(c.nitem)); HG_CUDA_TRY(vals_s.alloc(c.nitem));
   HG_CUDA_TRY(keys.alloc(c.nitem)); HG_CUDA_TRY(keys_s.alloc(c.nitem));
-  sched_b_kernel<<<GRID(c.GB), 0, s>>>(c.GB, c.GA, bpi, lagB, p->st_runA, (int32_t)p->st_nrunA, p->st_runB,
-                                      (int32_t)p->st_nrunB, p->st_needB, a_after.p, need_blk.p);
+  sched_b_kernel<<<GRID(c.GB), 0, s>>>(c.GB, c.GA, bpi, lagB, p->rg_runA, (int32_t)p->rg_nrunA, p->rg_runB,
+                                      (int32_t)p->rg_nrunB, p->st_needB, a_after.p, need_blk.p);
   const int32_t gmax = c.GA > c.GB ? c.GA : c.GB;
   sched_keys_kernel<<<GRID(gmax), 0, s>>>(c.GA, c.GB, c.GC, lagC, a_after.p, keys.p, vals.p);
   HG_CUDA_TRY(cudaGetLastError());
@@ -749,8 +760,8 @@ int get_sched(hgPlan *p, int bpi, int lagB, int lagC, int nslab, int discard, cu
   DevBuf<char> ws;
   HG_CUDA_TRY(ws.alloc(bytes));
   HG_CUDA_TRY(cub::DeviceRadixSort::SortPairs(ws.p, bytes, keys.p, keys_s.p, vals.p, vals_s.p, c.nitem, 0, 64, s));
-  sched_items_kernel<<<GRID(c.nitem), 0, s>>>(c.nitem, vals_s.p, bpi, p->st_runA, (int32_t)p->st_nrunA, p->st_runB,
-                                             (int32_t)p->st_nrunB, need_blk.p, p->rg_dlast, (int32_t)p->num_edges, c.GC,
+  sched_items_kernel<<<GRID(c.nitem), 0, s>>>(c.nitem, vals_s.p, bpi, ksub, p->rg_runA, (int32_t)p->rg_nrunA, p->rg_runB,
+                                             (int32_t)p->rg_nrunB, need_blk.p, p->rg_dlast, (int32_t)p->num_edges, c.GC,
                                              c.items);
   HG_CUDA_TRY(cudaGetLastError());
   HG_CUDA_TRY(cudaStreamSynchronize(s));
@@ -758,6 +769,8 @@ int get_sched(hgPlan *p, int bpi, int lagB, int lagC, int nslab, int discard, cu
   *out = &p->rg_sched[p->rg_nsched++];
   return HG_OK;
 }
+
+namespace {
 
 __global__ void zero_rows_kernel(int64_t nrows, const int32_t *__restrict__ segs, const int32_t *__restrict__ seg_edge,
                                  float *__restrict__ xe, int F) {
@@ -780,7 +793,7 @@ int launch_vpl(const RingArgs &ra, bool has_win, unsigned grid, unsigned threads
 }  // namespace
 
 void ring_free(hgPlan *p) {
-  cudaFree(p->rg_dperm); cudaFree(p->rg_dlast);
+  cudaFree(p->rg_dperm); cudaFree(p->rg_dlast); cudaFree(p->rg_runA); cudaFree(p->rg_runB);
   for (int i = 0; i < p->rg_nsched; ++i) { cudaFree(p->rg_sched[i].items); cudaFree(p->rg_sched[i].ctrl); }
   p->rg_nsched = 0;
 }
@@ -788,8 +801,8 @@ void ring_free(hgPlan *p) {
 bool ring_available(const hgPlan *plan, int F, bool force) {
   if (!plan->st_ready || F % 4 != 0) return false;
   if (force) return true;
-  if (tune_get("ring", 1) == 0) return false;
-  if (F < 128) return false;   // narrower rows: several rows per warp load, the stream form
+  if (tune_get("ring", 0) == 0) return false;   // not chosen on its own (hgef_fstream.cu is faster)
+  if (F < 128) return false;   // narrower rows: several rows per warp load, the stream forms
   // below ~64 MB of Y everything is L2-resident anyway and the two-pass form has the lower latency
   if ((double)plan->num_nodes * F * 4.0 < 64.0 * 1048576.0) return false;
   return plan->max_vdeg <= 65536;
@@ -822,7 +835,7 @@ int launch_ring(hgPlan *p, const dev::Args &a, cudaStream_t s) {
   if (ch < 1) ch = 1;
   if (ch > 32) ch = 32;
   int item_kb = tune_get("ring_item_kb", 32);
-  int bpi = item_kb * 1024 / (kL0 * slot_bytes);
+  int bpi = item_kb * 1024 / (kL0f * slot_bytes);
   if (bpi < 1) bpi = 1;
   const int grid = p->sm_count * ctas;
   int lagB = tune_get("ring_lag_b", -1), lagC = tune_get("ring_lag_c", -1);
@@ -832,14 +845,14 @@ int launch_ring(hgPlan *p, const dev::Args &a, cudaStream_t s) {
   const int discard = (F % 32 == 0 && tune_get("ring_discard", 1) != 0) ? 1 : 0;
 
   hgPlan::RingSched *sc = nullptr;
-  if (int rc = get_sched(p, bpi, lagB, lagC, nslab, discard, s, &sc)) return rc;
+  if (int rc = fused_get_sched(p, bpi, lagB, lagC, nslab, discard, 1, s, &sc)) return rc;
   if (p->nheavy_segs > 0) {
     zero_rows_kernel<<<(unsigned)ceil_div<int64_t>(p->nheavy_segs * 32, 256), 256, 0, s>>>(
         p->nheavy_segs, p->heavy_segs, p->seg_edge, p->xe, F);
     HG_CUDA_TRY(cudaGetLastError());
     ++p->kernels_launched;
   }
-  HG_CUDA_TRY(cudaMemsetAsync(sc->ctrl, 0, ((size_t)kCtrlHdr + (size_t)(sc->nblkA + sc->nblkB) * nslab) * sizeof(int32_t), s));
+  HG_CUDA_TRY(cudaMemsetAsync(sc->ctrl, 0, ((size_t)kCntOff + (size_t)(sc->nblkA + sc->nblkB) * nslab) * sizeof(int32_t), s));
   RingArgs ra{};
   ra.src[0] = p->st_srcA; ra.dst[0] = p->st_dstA; ra.src[1] = p->st_srcB; ra.dst[1] = p->st_dstB;
   ra.in[0] = a.X; ra.out[0] = p->xe; ra.in[1] = p->xe; ra.out[1] = a.Y;
@@ -870,18 +883,21 @@ int launch_ring(hgPlan *p, const dev::Args &a, cudaStream_t s) {
 int ring_debug(hgPlan *plan, int32_t *out8, cudaStream_t s) {
   for (int i = 0; i < 8; ++i) out8[i] = 0;
   if (!plan->rg_last_ctrl) return HG_OK;
-  HG_CUDA_TRY(cudaMemcpyAsync(out8, plan->rg_last_ctrl, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  int32_t h[kCntOff];
+  HG_CUDA_TRY(cudaMemcpyAsync(h, plan->rg_last_ctrl, kCntOff * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   HG_CUDA_TRY(cudaStreamSynchronize(s));
+  out8[0] = h[0]; out8[1] = h[kFlagOff];
+  for (int i = 0; i < 6; ++i) out8[2 + i] = h[kDbgOff + i];
   return HG_OK;
 }
 
 int ring_check(hgPlan *plan, cudaStream_t s) {
   if (!plan->rg_last_ctrl) return HG_OK;
   int32_t stalled = 0;
-  HG_CUDA_TRY(cudaMemcpyAsync(&stalled, plan->rg_last_ctrl + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  HG_CUDA_TRY(cudaMemcpyAsync(&stalled, plan->rg_last_ctrl + kFlagOff, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   HG_CUDA_TRY(cudaStreamSynchronize(s));
   if (stalled)
-    return set_error(HG_ECUDA, "ring aggregation: an item gave up waiting for its dependencies; the last result is invalid");
+    return set_error(HG_ECUDA, "fused aggregation: an item gave up waiting for its dependencies; the last result is invalid");
   return HG_OK;
 }
 

@@ -32,18 +32,13 @@
 
 #include <cstdlib>
 
-#include "hgef_aggr.cuh"
+#include "hgef_stream.cuh"
 
 namespace hg {
 namespace {
 using namespace dev;
 
-// dst word: bit31 = last member of its unit, bit30 = heavy (reduce into the row), low 30 bits = output row
-constexpr uint32_t kEnd = 0x80000000u, kHeavy = 0x40000000u, kIdMask = 0x3fffffffu, kRowMask = kIdMask;
-constexpr int kL0 = 16;      // positions per base run
-constexpr int kBlk = 8;      // A items per completion counter
 constexpr int kVec = 8;      // 128-bit row loads in flight per lane
-constexpr int kCtrlHdr = 8;  // ctrl[0] ticket counter, ctrl[1] give-up flag, ctrl[8..] block counts per slab
 
 struct StreamArgs {
   const int32_t *src[2], *dst[2], *run[2];   // row programs: [0] stage A, [1] stage B
@@ -62,6 +57,7 @@ struct StreamArgs {
   int32_t stage;                             // unfused: the stage this launch runs
   int32_t nblk, GA;                          // fused: completion blocks per slab, A items
   int32_t y_stream;                          // stage-B output stores carry the streaming (evict-first) hint
+  int32_t batch;                             // tickets claimed per atomic (two-launch form)
 };
 
 __device__ __forceinline__ int ld_relaxed_i32(const int *p) {
@@ -121,10 +117,16 @@ __global__ void __launch_bounds__(kThreads, MINB) stream_kernel(const StreamArgs
 #pragma unroll
   for (int q = 0; q < G::kSub; ++q) pat |= 1u << (q * SW);
 
+  int t_next = 0, t_left = 0;
   for (;;) {
-    int t = 0;
-    if (lane == 0) t = atomicAdd(sa.ctrl, 1);
-    t = __shfl_sync(kFull, t, 0);
+    if (t_left == 0) {   // tickets are claimed `batch` at a time (the counter is one address for the whole grid)
+      int tb = 0;
+      if (lane == 0) tb = atomicAdd(sa.ctrl, sa.batch);
+      t_next = __shfl_sync(kFull, tb, 0);
+      t_left = sa.batch;
+    }
+    const int t = t_next++;
+    --t_left;
     if (t >= total) break;
     const int slab = sa.nslab > 1 ? t / sa.nitem : 0;
     const int k = t - slab * sa.nitem;
@@ -341,13 +343,13 @@ __global__ void prog_fill_kernel(int64_t nunit, const int32_t *__restrict__ ptr_
   }
 }
 
-// run[r] = smallest unit start >= r * kL0 (units are never cut); run[nrun] = npos
+// run[r] = smallest unit start >= r * L0 (units are never cut); run[nrun] = npos
 __global__ void run_ptr_kernel(int64_t nrun, int64_t nunit, const int32_t *__restrict__ ptr, int64_t npos,
-                               int32_t *__restrict__ run) {
+                               int32_t *__restrict__ run, int L0) {
   const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r > nrun) return;
   if (r == nrun) { run[r] = (int32_t)npos; return; }
-  const int64_t target = r * kL0;
+  const int64_t target = r * L0;
   int64_t lo = 0, hi = nunit;          // first unit index with ptr[idx] >= target (ptr[nunit] = npos >= target)
   while (lo < hi) {
     const int64_t mid = (lo + hi) >> 1;
@@ -463,7 +465,7 @@ int env_int(const char *name, int dflt) {
 void stream_free(hgPlan *p) {
   cudaFree(p->st_srcA); cudaFree(p->st_dstA); cudaFree(p->st_runA);
   cudaFree(p->st_srcB); cudaFree(p->st_dstB); cudaFree(p->st_needB); cudaFree(p->st_runB);
-  cudaFree(p->st_perm); cudaFree(p->st_ctrl);
+  cudaFree(p->st_perm); cudaFree(p->st_ctrl); cudaFree(p->st_ptrB);
   for (int i = 0; i < p->st_nsched; ++i) { cudaFree(p->st_sched[i].sched); cudaFree(p->st_sched[i].ctrl); }
   p->st_nsched = 0;
 }
@@ -487,13 +489,14 @@ int build_stream(hgPlan *p, cudaStream_t s) {
   if (int rc = dev_alloc(&p->st_runA, p->st_nrunA + 1)) return rc;
   prog_fill_kernel<<<(unsigned)ceil_div<int64_t>(S * 32, 256), 256, 0, s>>>(
       S, p->key, p->key, nullptr, p->colind, p->seg_edge, p->seg_slot, nullptr, p->st_srcA, p->st_dstA, nullptr);
-  run_ptr_kernel<<<GRID(p->st_nrunA + 1), 0, s>>>(p->st_nrunA, S, p->key, Z, p->st_runA);
+  run_ptr_kernel<<<GRID(p->st_nrunA + 1), 0, s>>>(p->st_nrunA, S, p->key, Z, p->st_runA, kL0);
   HG_CUDA_TRY(cudaGetLastError());
 
   // stage B: units = vertices, ordered by their last hyperedge (the stage-A position they wait for)
-  DevBuf<int32_t> keys, ids, keys_s, edge_end, deg, ptrB, unit_need;
+  DevBuf<int32_t> keys, ids, keys_s, edge_end, deg, unit_need;
   HG_CUDA_TRY(keys.alloc(N)); HG_CUDA_TRY(ids.alloc(N)); HG_CUDA_TRY(keys_s.alloc(N));
-  HG_CUDA_TRY(edge_end.alloc(M + 1)); HG_CUDA_TRY(deg.alloc(N + 1)); HG_CUDA_TRY(ptrB.alloc(N + 1));
+  HG_CUDA_TRY(edge_end.alloc(M + 1)); HG_CUDA_TRY(deg.alloc(N + 1));
+  if (int rc = dev_alloc(&p->st_ptrB, N + 1)) return rc;
   HG_CUDA_TRY(unit_need.alloc(N));
   if (int rc = dev_alloc(&p->st_perm, N)) return rc;
   HG_CUDA_TRY(cudaMemsetAsync(edge_end.p, 0, (size_t)(M + 1) * sizeof(int32_t), s));
@@ -514,10 +517,10 @@ int build_stream(hgPlan *p, cudaStream_t s) {
   HG_CUDA_TRY(cudaGetLastError());
   {
     size_t b2 = 0;
-    HG_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, b2, deg.p, ptrB.p, N + 1, s));
+    HG_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, b2, deg.p, p->st_ptrB, N + 1, s));
     DevBuf<char> ws;
     HG_CUDA_TRY(ws.alloc(b2));
-    HG_CUDA_TRY(cub::DeviceScan::ExclusiveSum(ws.p, b2, deg.p, ptrB.p, N + 1, s));
+    HG_CUDA_TRY(cub::DeviceScan::ExclusiveSum(ws.p, b2, deg.p, p->st_ptrB, N + 1, s));
     HG_CUDA_TRY(cudaStreamSynchronize(s));
   }
   // isolated vertices are the tail of the permutation (sorted key == M)
@@ -541,11 +544,23 @@ int build_stream(hgPlan *p, cudaStream_t s) {
   const int64_t NB = p->st_nunitB;
   if (NB > 0)
     prog_fill_kernel<<<(unsigned)ceil_div<int64_t>(NB * 32, 256), 256, 0, s>>>(
-        NB, p->h_ptr, ptrB.p, p->st_perm, p->h_ind, nullptr, nullptr, unit_need.p, p->st_srcB, p->st_dstB, p->st_needB);
-  run_ptr_kernel<<<GRID(p->st_nrunB + 1), 0, s>>>(p->st_nrunB, NB, ptrB.p, Z, p->st_runB);
+        NB, p->h_ptr, p->st_ptrB, p->st_perm, p->h_ind, nullptr, nullptr, unit_need.p, p->st_srcB, p->st_dstB, p->st_needB);
+  run_ptr_kernel<<<GRID(p->st_nrunB + 1), 0, s>>>(p->st_nrunB, NB, p->st_ptrB, Z, p->st_runB, kL0);
   HG_CUDA_TRY(cudaGetLastError());
   HG_CUDA_TRY(cudaStreamSynchronize(s));
   p->st_ready = 1;
+  return HG_OK;
+}
+
+// unit-aligned run tables of both stages for runs of L0 positions (the fused forms use finer runs than kL0)
+int stream_build_runs(hgPlan *p, int L0, int32_t **runA, int64_t *nrunA, int32_t **runB, int64_t *nrunB, cudaStream_t s) {
+  const int64_t Z = p->nnz;
+  *nrunA = *nrunB = ceil_div<int64_t>(Z, L0);
+  if (int rc = dev_alloc(runA, *nrunA + 1)) return rc;
+  if (int rc = dev_alloc(runB, *nrunB + 1)) return rc;
+  run_ptr_kernel<<<GRID(*nrunA + 1), 0, s>>>(*nrunA, p->nseg, p->key, Z, *runA, L0);
+  run_ptr_kernel<<<GRID(*nrunB + 1), 0, s>>>(*nrunB, p->st_nunitB, p->st_ptrB, Z, *runB, L0);
+  HG_CUDA_TRY(cudaGetLastError());
   return HG_OK;
 }
 
@@ -632,8 +647,6 @@ bool stream_available(const hgPlan *plan, int F, bool force) {
   return plan->max_vdeg <= 65536;   // one sub-warp walks a vertex's hyperedges
 }
 
-int ensure_xe(hgPlan *plan, int F, cudaStream_t s);
-
 int launch_stream(hgPlan *p, const dev::Args &a, cudaStream_t s) {
   const int F = a.F;
   if (int rc = ensure_xe(p, F, s)) return rc;
@@ -684,6 +697,8 @@ int launch_stream(hgPlan *p, const dev::Args &a, cudaStream_t s) {
   sa.iso = p->st_perm + p->st_nunitB; sa.niso = (int32_t)p->st_niso;
   sa.nslab = cfg.nslab; sa.slabF = cfg.slabF; sa.F = F; sa.k0 = cfg.k0;
   sa.y_stream = env_int("HGEF_ST_CS", 1);
+  sa.batch = cfg.fused ? 1 : tune_get("st_batch", 1);
+  if (sa.batch < 1) sa.batch = 1;
   const int32_t GA = (int32_t)ceil_div<int64_t>(p->st_nrunA, bpi), GB = (int32_t)ceil_div<int64_t>(p->st_nrunB, bpi);
 
   if (cfg.fused) {

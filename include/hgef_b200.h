@@ -146,6 +146,9 @@ enum {
                             no reductions; the earlier form, kept for A/B) */
   HG_FORCE_STREAM = 64,  /* always the stream form: both stages as register-only row streams, two launches, the
                             hyperedge features make a round trip through HBM */
+  HG_FORCE_FSTREAM = 256, /* always the fused stream form: both stages as register-only row streams in ONE persistent
+                            launch, hyperedge features handed over through the L2 and discarded there (the form chosen
+                            when Y exceeds the L2) */
   HG_FORCE_RING = 128    /* always the ring form: both stages in one persistent launch, rows moved by TMA bulk copies
                             into a shared-memory ring, hyperedge features handed over through the L2 and discarded
                             there (the form chosen for rows >= 512 B when Y exceeds the L2) */

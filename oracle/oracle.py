@@ -275,6 +275,41 @@ def ref_hyperaggr_host(indptr, indices, t_indptr, t_indices, X) -> np.ndarray:
     return Y
 
 
+def ref_lab_gpu(variant: int, ngs: int, num_edges: int, key, st, ed, t_indices, X, out=None, iters: int = 0):
+    """The reference's own lab kernels on the GPU, compiled in place for sm_100a (oracle/ref_shim.cu):
+    variant 0 = HyperGAggr_Edgefused_Balance_Full_Kernel (`edge_based_full`, include/hgnnAgg.cuh:98-131,
+    launch geometry :985-1003), 1 = ..._Shm_Kernel (`edge_based_shm`, :170-276, :1004-1017).  Un-scaled
+    operator Y = H H^T X over the balancer groups; all arguments are CUDA tensors (int32 / float32).
+    F must be < 32 or a multiple of 32 (the reference's own restriction).  With iters > 0 returns
+    (Y, microseconds per call) timed the way the extension runs (zero-fill + kernel, hgnnaggr_cuda.cu:374),
+    back to back on the legacy default stream."""
+    lib_ = ref_lib()
+    fn = lib_.ref_lab_full_gpu
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_int] * 5 + [C.c_void_p] * 6
+    F = int(X.shape[1])
+    Y = torch.zeros_like(X) if out is None else out
+
+    def launch():
+        Y.zero_()
+        rc = fn(int(variant), int(num_edges), int(ngs), int(st.numel()), F, key.data_ptr(), st.data_ptr(),
+                ed.data_ptr(), t_indices.data_ptr(), X.data_ptr(), Y.data_ptr())
+        if rc != 0:
+            raise RuntimeError(f"reference lab kernel launch failed: cudaError {rc}")
+    torch.cuda.synchronize()
+    launch()
+    torch.cuda.synchronize()
+    if iters <= 0:
+        return Y
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        launch()
+    b.record()
+    torch.cuda.synchronize()
+    return Y, a.elapsed_time(b) / iters * 1e3
+
+
 def ref_weight_grad(t_indptr, t_indices, G, X) -> np.ndarray:
     """The reference's hgnnbp_reference_host (check.cuh:116-143), compiled in place."""
     t_indptr, t_indices = _i32(t_indptr), _i32(t_indices)
@@ -362,6 +397,18 @@ def rel_err(got, want64) -> float:
     want64 = np.asarray(want64, dtype=np.float64)
     scale = max(float(np.abs(want64).max()) if want64.size else 0.0, 1e-30)
     return float(np.abs(got - want64).max() / scale) if want64.size else 0.0
+
+
+def rel_err_terms(got, want64, bound64, eps: float = 1e-30) -> float:
+    """Element-wise error scaled by the sum of the magnitudes of the terms of each output element
+    (SURVEY.md 7.3-4): max_ij |got - want| / bound, bound_ij = sum |terms| (the same aggregation applied
+    to |X| with |scales|).  Tighter than rel_err: an element is not excused by a large value elsewhere."""
+    got = np.asarray(got, dtype=np.float64)
+    want64 = np.asarray(want64, dtype=np.float64)
+    bound64 = np.asarray(bound64, dtype=np.float64)
+    if want64.size == 0:
+        return 0.0
+    return float((np.abs(got - want64) / np.maximum(bound64, eps)).max())
 
 
 def ref_read_mtx(path):

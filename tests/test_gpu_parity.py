@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-5
 
 
-@pytest.fixture(params=["auto", "fused", "two_pass", "pull", "stream", "stream2", "ring"])
+@pytest.fixture(params=["auto", "fused", "two_pass", "pull", "stream", "stream2", "ring", "fstream"])
 def kernel_form(request):
     """Run a test with the library's own choice of kernel form, then with each form forced
     (the large-graph forms are only chosen on their own when Y exceeds the L2).  "stream" is the
@@ -27,7 +27,8 @@ def kernel_form(request):
     import os
     ops.DEFAULT_FLAGS = {"auto": 0, "fused": _native.HG_FORCE_FUSED, "two_pass": _native.HG_TWO_PASS,
                          "pull": _native.HG_FORCE_PULL, "stream": _native.HG_FORCE_STREAM,
-                         "stream2": _native.HG_FORCE_STREAM, "ring": _native.HG_FORCE_RING}[request.param]
+                         "stream2": _native.HG_FORCE_STREAM, "ring": _native.HG_FORCE_RING,
+                         "fstream": _native.HG_FORCE_FSTREAM}[request.param]
     if request.param in ("stream", "stream2"):
         os.environ["HGEF_ST_FUSED"] = "1" if request.param == "stream" else "0"
     yield request.param
@@ -368,12 +369,56 @@ def test_ring_form_configurations(shape, replicas, cuda_device):
         ops.tune(**{k: None for k in RING_KNOBS})
 
 
-@pytest.mark.parametrize("form", ["two_pass", "stream", "stream_fused", "fused", "pull", "ring"])
+FS_KNOBS = ("fs_batch", "fs_sw", "fs_occ", "fs_pipe", "fs_ctas", "fs_item_kb", "fs_lag_b", "fs_lag_c", "fs_discard", "fs_pol_x", "fs_pol_xe_w",
+            "fs_pol_y")
+
+
+@pytest.mark.parametrize("shape,replicas", [("pubmed", 3), ("walmart", 1), ("dblp", 2)])
+def test_fused_stream_form_configurations(shape, replicas, cuda_device):
+    """The fused stream form (one persistent launch: register row streams, A / B / discard items in one
+    ticket order) under every knob -- sub-warp width, occupancy, pipelining, item size, lags down to 0
+    (dependencies really wait), discard on / off, eviction hints -- forward and transposed, EVERY feature
+    length against the fp64 C oracle; bit-identical run to run where the graph has no heavy hyperedge."""
+    data = synth.make_shape(shape, replicas=replicas, seed=3)
+    hg = HyperGraph(data, cuda_device, data.dataset)
+    N, M = hg.num_nodes, hg.num_edges
+    plan = ops.get_plan(hg.group_key, hg.group_row, hg.group_start, hg.group_end, hg.H_T_colind, N, M)
+    W = torch.rand(M, device=cuda_device) + 0.5
+    ptr, ind = _np(hg.H_T_csrptr), _np(hg.H_T_colind)
+    combos = [dict(), dict(fs_lag_b=0, fs_lag_c=0), dict(fs_occ=2, fs_item_kb=4), dict(fs_occ=1, fs_pipe=0, fs_batch=1),
+              dict(fs_sw=16, fs_item_kb=1, fs_lag_b=5, fs_lag_c=2), dict(fs_sw=8, fs_ctas=1, fs_item_kb=64),
+              dict(fs_discard=0, fs_lag_b=1000000), dict(fs_pol_x=0, fs_pol_xe_w=0, fs_pol_y=0, fs_pipe=1),
+              dict(fs_item_kb=256, fs_ctas=2)]
+    try:
+        for F in (4, 20, 32, 64, 100, 128, 256, 384, 512, 640, 1056):
+            X = torch.randn(N, F, device=cuda_device)
+            s_edge = _np(hg.degE).ravel() * _np(W)
+            want = orc.c_aggr_formula(ptr, ind, X.cpu(), s1=s_edge, a_out=_np(hg.degV))
+            want_t = orc.c_aggr_formula(ptr, ind, X.cpu(), s1=s_edge, a_in=_np(hg.degV))
+            for knobs in combos:
+                ops.tune(**{k: None for k in FS_KNOBS})
+                ops.tune(**knobs)
+                out = torch.full((N, F), float("nan"), device=cuda_device)
+                ops.aggregate(plan, X, s1=hg.degE, s2=W, a_out=hg.degV, out=out, flags=_native.HG_FORCE_FSTREAM)
+                plan.check()
+                assert orc.rel_err(_np(out), want) < TOL, (shape, F, knobs)
+                out_t = ops.aggregate(plan, X, s1=hg.degE, s2=W, a_in=hg.degV, flags=_native.HG_FORCE_FSTREAM)
+                assert orc.rel_err(_np(out_t), want_t) < TOL, (shape, F, knobs, "transposed")
+                if plan.nheavy_edges == 0:
+                    again = ops.aggregate(plan, X, s1=hg.degE, s2=W, a_out=hg.degV, flags=_native.HG_FORCE_FSTREAM)
+                    assert torch.equal(again, out), (shape, F, knobs, "run-to-run")
+                plan.check()
+    finally:
+        ops.tune(**{k: None for k in FS_KNOBS})
+
+
+@pytest.mark.parametrize("form", ["two_pass", "stream", "stream_fused", "fused", "pull", "ring", "fstream"])
 def test_cuda_graph_capture_and_replay(form, cuda_device, monkeypatch):
     """Every kernel form is capture-safe after one eager warm-up call (the first call of a plan may allocate its
     scratch): a captured aggregation replays correctly on new contents of the same input buffer."""
     flags = {"two_pass": _native.HG_TWO_PASS, "stream": _native.HG_FORCE_STREAM, "stream_fused": _native.HG_FORCE_STREAM,
-             "fused": _native.HG_FORCE_FUSED, "pull": _native.HG_FORCE_PULL, "ring": _native.HG_FORCE_RING}[form]
+             "fused": _native.HG_FORCE_FUSED, "pull": _native.HG_FORCE_PULL, "ring": _native.HG_FORCE_RING,
+             "fstream": _native.HG_FORCE_FSTREAM}[form]
     if form == "stream_fused":
         monkeypatch.setenv("HGEF_ST_FUSED", "1")
     data = synth.make_shape("pubmed", replicas=2, seed=5)
@@ -555,7 +600,7 @@ def test_ragged_and_degenerate_graphs(cuda_device):
             out = torch.full((N, F), float("nan"), device=cuda_device)
             plan = ops.get_plan(hg.group_key, hg.group_row, hg.group_start, hg.group_end, hg.H_T_colind, N, hg.num_edges)
             for flags in (0, _native.HG_TWO_PASS, _native.HG_FORCE_FUSED, _native.HG_FORCE_PULL, _native.HG_FORCE_STREAM,
-                          _native.HG_FORCE_RING):
+                          _native.HG_FORCE_RING, _native.HG_FORCE_FSTREAM):
                 ops.aggregate(plan, X.to(cuda_device), s1=hg.degE, a_out=hg.degV, out=out, flags=flags)
                 assert orc.rel_err(_np(out), want) < TOL or np.abs(want).max() == 0, (len(members), N, ngs, F, flags)
             plan.check()

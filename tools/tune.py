@@ -16,6 +16,7 @@ ap.add_argument("--force-fused", action="store_true")
 ap.add_argument("--force-pull", action="store_true")
 ap.add_argument("--force-stream", action="store_true")
 ap.add_argument("--force-ring", action="store_true")
+ap.add_argument("--force-fstream", action="store_true")
 ap.add_argument("--tag", default="")
 ap.add_argument("--sweep", default="", help="semicolon-separated env configs K=V,K=V applied in-process (stream form knobs are read per call)")
 args = ap.parse_args()
@@ -25,7 +26,7 @@ hg = hgef.HyperGraph(data, dev, data.dataset)
 N, M, Z = hg.num_nodes, hg.num_edges, hg.H_T_colind.numel()
 plan = ops.get_plan(hg.group_key, hg.group_row, hg.group_start, hg.group_end, hg.H_T_colind, N, M)
 W = torch.ones(M, device=dev)
-flags = _native.HG_TWO_PASS if args.two_pass else (_native.HG_FORCE_FUSED if args.force_fused else (_native.HG_FORCE_PULL if args.force_pull else (_native.HG_FORCE_STREAM if args.force_stream else (_native.HG_FORCE_RING if args.force_ring else 0))))
+flags = _native.HG_TWO_PASS if args.two_pass else (_native.HG_FORCE_FUSED if args.force_fused else (_native.HG_FORCE_PULL if args.force_pull else (_native.HG_FORCE_STREAM if args.force_stream else (_native.HG_FORCE_RING if args.force_ring else (_native.HG_FORCE_FSTREAM if args.force_fstream else 0)))))
 TUNED = set()
 KNOBS = ("HGEF_ST_FUSED", "HGEF_ST_L", "HGEF_ST_LAG", "HGEF_ST_SLAB", "HGEF_ST_CTAS", "HGEF_ST_ONLY", "HGEF_ST_OCC", "HGEF_ST_CS", "HGEF_ST_SW", "HGEF_ST_PIPE")
 for cfg in (args.sweep.split(";") if args.sweep else [""]):
@@ -35,7 +36,7 @@ for cfg in (args.sweep.split(";") if args.sweep else [""]):
     TUNED.clear()
     for kv in filter(None, cfg.split(",")):
         k, v = kv.split("=")
-        if k.startswith("ring") or k.startswith("st_"):     # hg_tune_set knobs
+        if k.startswith("ring") or k.startswith("fs_") or k.startswith("st_") or k == "fstream":     # hg_tune_set knobs
             ops.tune(**{k: int(v)})
             TUNED.add(k)
         else:

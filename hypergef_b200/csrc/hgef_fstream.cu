@@ -128,10 +128,11 @@ __device__ __forceinline__ void stream_run(const FArgs &fa, int32_t ps, int32_t 
   for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
   int32_t cb = ps;
   uint32_t c_src = 0, c_dst = 0;
-  if (cb + sl < pe) {
-    c_src = (uint32_t)__ldg(src + cb + sl);
-    c_dst = (uint32_t)__ldg(dst + cb + sl);
-  }
+  auto fetch = [&](int32_t p, uint32_t &ws, uint32_t &wdst) {
+    ws = (uint32_t)__ldg(src + p);
+    wdst = (uint32_t)__ldg(dst + p);
+  };
+  if (cb + sl < pe) fetch(cb + sl, c_src, c_dst);
   float4 x0[HB][VPL], x1[HB][VPL];
   // (positions past the end of the run carry src word 0: row 0 is loaded and never used for output -- a run
   //  ends with a unit end, which resets `acc`)
@@ -157,10 +158,7 @@ __device__ __forceinline__ void stream_run(const FArgs &fa, int32_t ps, int32_t 
     }
     const uint32_t endm = __ballot_sync(kFull, (c_dst & kEnd) != 0);
     uint32_t n_src = 0, n_dst = 0;   // next chunk's words: in flight while this chunk streams
-    if (cb + SW + sl < pe) {
-      n_src = (uint32_t)__ldg(src + cb + SW + sl);
-      n_dst = (uint32_t)__ldg(dst + cb + SW + sl);
-    }
+    if (cb + SW + sl < pe) fetch(cb + SW + sl, n_src, n_dst);
     auto consume_half = [&](const float4(&x)[HB][VPL], int j0) {
 #pragma unroll
       for (int u = 0; u < HB; ++u) {
@@ -363,6 +361,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fstream_kernel(const __grid_co
     t = tn; slab = nslab_i; ia = na; ib = nb;
   }
 }
+
 
 struct FCfg { int sw, vpl, occ, kv; bool pipe; };
 

@@ -385,10 +385,10 @@ def test_fused_stream_form_configurations(shape, replicas, cuda_device):
     plan = ops.get_plan(hg.group_key, hg.group_row, hg.group_start, hg.group_end, hg.H_T_colind, N, M)
     W = torch.rand(M, device=cuda_device) + 0.5
     ptr, ind = _np(hg.H_T_csrptr), _np(hg.H_T_colind)
-    combos = [dict(), dict(fs_lag_b=0, fs_lag_c=0), dict(fs_occ=2, fs_item_kb=4), dict(fs_occ=1, fs_pipe=0, fs_batch=1),
-              dict(fs_sw=16, fs_item_kb=1, fs_lag_b=5, fs_lag_c=2), dict(fs_sw=8, fs_ctas=1, fs_item_kb=64),
+    combos = [dict(), dict(fs_lag_b=0, fs_lag_c=0, fs_batch=1), dict(fs_occ=2, fs_item_kb=4), dict(fs_occ=1, fs_pipe=0, fs_batch=1),
+              dict(fs_sw=16, fs_item_kb=1, fs_lag_b=5, fs_lag_c=2, fs_batch=8), dict(fs_sw=8, fs_ctas=1, fs_item_kb=64),
               dict(fs_discard=0, fs_lag_b=1000000), dict(fs_pol_x=0, fs_pol_xe_w=0, fs_pol_y=0, fs_pipe=1),
-              dict(fs_item_kb=256, fs_ctas=2)]
+              dict(fs_item_kb=256, fs_ctas=2, fs_batch=2)]
     try:
         for F in (4, 20, 32, 64, 100, 128, 256, 384, 512, 640, 1056):
             X = torch.randn(N, F, device=cuda_device)

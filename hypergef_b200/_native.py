@@ -48,6 +48,7 @@ SIGNATURES = {
     "hg_plan_create": [C.POINTER(_vp), _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _int, _vp],
     "hg_plan_destroy": [_vp],
     "hg_plan_info": [_vp, _pi64, _pi64, _pi64, _pi32],
+    "hg_plan_reserve": [_vp, _i32, _vp],
     "hg_plan_debug": [_vp, _pi32, _vp],
     "hg_plan_check": [_vp, _vp],
     "hg_plan_launches": [_vp, _pi64],

@@ -14,7 +14,7 @@ import torch.nn.functional as F
 
 from .wrappers import HGNNAggr, UniGNNConv, UniGNNConvdeg
 
-__all__ = ["HyperGsysHGNN", "HyperGsysUinGINConv", "HyperGsysUniGCNIIConv", "HGsysHGNN"]
+__all__ = ["HyperGsysHGNN", "HyperGsysUinGINConv", "HyperGsysUniGCNIIConv", "HGsysHGNN", "ColumnParallelHGNN"]
 
 
 class HyperGsysHGNN(nn.Module):
@@ -83,3 +83,47 @@ class HGsysHGNN(nn.Module):
         for conv in self.convs:
             X = self.dropout(self.act(conv(X)))
         return F.log_softmax(self.conv_out(X), dim=1)
+
+
+class _GatherColumns(torch.autograd.Function):
+    """all_gather of column blocks ``[N, F/P] -> [N, F]`` whose consumers are REPLICATED on every rank (each rank
+    then computes the same loss): the gradient of the local block is the matching column slice of the incoming
+    gradient, with no reduction across ranks."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        import torch.distributed as dist
+        world = dist.get_world_size(group)
+        ctx.rank, ctx.cols = dist.get_rank(group), x.shape[1]
+        parts = [torch.empty_like(x) for _ in range(world)]
+        dist.all_gather(parts, x.contiguous(), group=group)
+        return torch.cat(parts, dim=1)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g[:, ctx.rank * ctx.cols:(ctx.rank + 1) * ctx.cols].contiguous(), None
+
+
+class ColumnParallelHGNN(nn.Module):
+    """The 2-layer HGNN of ``model/gnn.py:110-134`` over ``P`` GPUs by FEATURE-COLUMN sharding:
+    the aggregation never mixes columns (``hgnnaggr_cuda.cu:21,34,44``), so rank r holds the replicated graph,
+    the replicated input features and the column block ``W1[:, r]`` of the first layer, aggregates its own
+    ``nhid / P`` hidden columns with no collective, and one ``all_gather`` of ``[N, nhid / P]`` activations
+    feeds the (small, replicated) output layer.  The reference is single-GPU (``hgsys.py:54``)."""
+
+    def __init__(self, hyperg, nfeat, nhid, nclass, group=None, input_drop=0.6, dropout=0.6):
+        super().__init__()
+        import torch.distributed as dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if nhid % self.world:
+            raise ValueError(f"nhid={nhid} is not divisible by the {self.world} ranks")
+        self.conv1 = HyperGsysHGNN(hyperg, nfeat, nhid // self.world)
+        self.conv_out = HyperGsysHGNN(hyperg, nhid, nclass)
+        self.input_drop, self.dropout = nn.Dropout(input_drop), nn.Dropout(dropout)
+
+    def forward(self, X):
+        h = torch.relu(self.conv1(self.input_drop(X)))
+        if self.world > 1:
+            h = _GatherColumns.apply(h, self.group)
+        return F.log_softmax(self.conv_out(self.dropout(h)), dim=1)

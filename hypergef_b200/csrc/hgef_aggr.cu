@@ -21,14 +21,16 @@
 #include "hgef_stream.cuh"
 
 namespace hg {
+#ifdef HGEF_LAB
 bool fused_available(const hgPlan *plan, int F, bool force);
 int launch_fused(hgPlan *plan, const dev::Args &base, cudaStream_t s);
 int fused_check(hgPlan *plan, cudaStream_t s);
 bool pull_available(const hgPlan *plan, int F, bool force);
 int launch_pull_any(hgPlan *plan, const dev::Args &base, cudaStream_t s);
+#endif
 bool stream_available(const hgPlan *plan, int F, bool force);
 int launch_stream(hgPlan *plan, const dev::Args &base, cudaStream_t s);
-int stream_check(hgPlan *plan, cudaStream_t s);
+int launch_stream_padded(hgPlan *plan, const dev::Args &base, cudaStream_t s);
 namespace {
 using namespace dev;
 
@@ -212,9 +214,15 @@ int hg_plan_launches(const hgPlan *plan, int64_t *kernels) {
 
 int hg_plan_debug(hgPlan *plan, int32_t *h_out8, void *stream) {
   HG_REQUIRE(plan != nullptr && h_out8 != nullptr, "plan_debug: NULL argument");
+  for (int i = 0; i < 8; ++i) h_out8[i] = 0;
+#ifdef HGEF_LAB
   DeviceGuard guard(plan->device);
   HG_REQUIRE(guard.ok(), "plan_debug: cannot select device %d", plan->device);
   return ring_debug(plan, h_out8, (cudaStream_t)stream);
+#else
+  (void)stream;
+  return HG_OK;
+#endif
 }
 
 int hg_plan_check(hgPlan *plan, void *stream) {
@@ -224,9 +232,24 @@ int hg_plan_check(hgPlan *plan, void *stream) {
   cudaStream_t s = (cudaStream_t)stream;
   HG_CUDA_TRY(cudaStreamSynchronize(s));
   HG_CUDA_TRY(cudaGetLastError());
-  if (int rc = stream_check(plan, s)) return rc;
+#ifdef HGEF_LAB
   if (int rc = ring_check(plan, s)) return rc;
-  return fused_check(plan, s);
+  if (int rc = fused_check(plan, s)) return rc;
+#endif
+  return HG_OK;
+}
+
+int hg_plan_reserve(hgPlan *plan, int32_t F_max, void *stream) {
+  HG_REQUIRE(plan != nullptr && F_max >= 1, "plan_reserve: bad argument");
+  DeviceGuard guard(plan->device);
+  HG_REQUIRE(guard.ok(), "plan_reserve: cannot select device %d", plan->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int Fp = (F_max + 3) / 4 * 4;
+  if (plan->canonical && plan->st_ready)
+    if (int rc = plan_grow(plan, &plan->xe, &plan->xe_floats, (size_t)plan->num_edges * Fp, s, "hyperedge features")) return rc;
+  if (plan->nheavy_edges > 0)
+    if (int rc = plan_grow(plan, &plan->scratch, &plan->scratch_floats, (size_t)plan->nheavy_edges * Fp, s, "heavy-hyperedge scratch")) return rc;
+  return HG_OK;
 }
 
 int hg_aggr_forward(hgPlan *plan, const float *d_X, const float *d_s1, const float *d_s2,
@@ -234,6 +257,11 @@ int hg_aggr_forward(hgPlan *plan, const float *d_X, const float *d_s1, const flo
                     void *stream) {
   HG_REQUIRE(plan != nullptr, "aggr_forward: plan is NULL");
   if (int rc = check_common(d_X, d_Y, F)) return rc;
+  constexpr int kLabForms = HG_FORCE_FUSED | HG_FORCE_PULL | HG_FORCE_RING | HG_FORCE_FSTREAM;
+#ifndef HGEF_LAB
+  HG_REQUIRE(!(flags & kLabForms), "aggr_forward: flags 0x%x select an experimental kernel form; those are only built "
+             "into libhgef_b200_lab.so (make -C hypergef_b200/csrc lab)", flags);
+#endif
   if (!plan->canonical)
     return hg_aggr_groups(plan->num_nodes, plan->ngroup, plan->key, plan->row, plan->st, plan->ed,
                           plan->colind, d_X, d_s1, d_s2, d_a_out, d_a_in, d_Y, F, flags, plan->device,
@@ -243,59 +271,39 @@ int hg_aggr_forward(hgPlan *plan, const float *d_X, const float *d_s1, const flo
   cudaStream_t s = (cudaStream_t)stream;
   const bool vec4 = F % 4 == 0 && !(flags & HG_FORCE_SCALAR) && aligned16(d_X) && aligned16(d_Y);
   const bool vec = vec4 && F <= 512;
-  // fused stream form: one persistent launch of register-only row streams, hyperedge features handed over
-  // through the L2 and discarded there (hgef_fstream.cu): the default when Y exceeds the L2
-  const bool use_fstream = vec4 && !(flags & (HG_ACCUMULATE | HG_TWO_PASS | HG_FORCE_FUSED | HG_FORCE_PULL | HG_FORCE_STREAM | HG_FORCE_RING)) &&
-                           fstream_available(plan, F, (flags & HG_FORCE_FSTREAM) != 0);
-  if (use_fstream) {
-    Args pa{};
-    pa.X = d_X; pa.s1 = d_s1; pa.s2 = d_s2; pa.a_out = d_a_out; pa.a_in = d_a_in; pa.Y = d_Y; pa.F = F;
-    return launch_fstream(plan, pa, s);
-  }
-  // ring form: the same schedule with TMA bulk row copies into a shared-memory ring (hgef_ring.cu)
-  const bool use_ring = vec4 && !(flags & (HG_ACCUMULATE | HG_TWO_PASS | HG_FORCE_FUSED | HG_FORCE_PULL | HG_FORCE_STREAM | HG_FORCE_FSTREAM)) &&
-                        ring_available(plan, F, (flags & HG_FORCE_RING) != 0);
-  if (use_ring) {
-    Args pa{};
-    pa.X = d_X; pa.s1 = d_s1; pa.s2 = d_s2; pa.a_out = d_a_out; pa.a_in = d_a_in; pa.Y = d_Y; pa.F = F;
-    return launch_ring(plan, pa, s);
-  }
-  // stream form: both stages as lean register-only row streams, two launches (hgef_stream.cu)
-  const bool use_stream = vec4 && !(flags & (HG_ACCUMULATE | HG_TWO_PASS | HG_FORCE_FUSED | HG_FORCE_PULL | HG_FORCE_RING | HG_FORCE_FSTREAM)) &&
-                      stream_available(plan, F, (flags & HG_FORCE_STREAM) != 0);
-  if (use_stream) {
-    Args pa{};
-    pa.X = d_X; pa.s1 = d_s1; pa.s2 = d_s2; pa.a_out = d_a_out; pa.a_in = d_a_in; pa.Y = d_Y; pa.F = F;
-    return launch_stream(plan, pa, s);
-  }
-  // single-launch persistent form: zero-fill happens inside the kernel (hgef_fused.cu)
-  // gather-only two-phase form (no reductions): the fastest when it applies (hgef_fused.cu)
-  const bool pull = vec && !(flags & (HG_ACCUMULATE | HG_TWO_PASS | HG_FORCE_FUSED)) &&
-                    pull_available(plan, F, (flags & HG_FORCE_PULL) != 0);
-  if (pull) {
-    Args pa{};
-    pa.X = d_X; pa.s1 = d_s1; pa.s2 = d_s2; pa.a_out = d_a_out; pa.a_in = d_a_in; pa.Y = d_Y; pa.F = F;
+  const bool plain = !(flags & (HG_ACCUMULATE | HG_TWO_PASS | kLabForms));
+  Args pa{};
+  pa.X = d_X; pa.s1 = d_s1; pa.s2 = d_s2; pa.a_out = d_a_out; pa.a_in = d_a_in; pa.Y = d_Y; pa.F = F;
+#ifdef HGEF_LAB
+  // experimental forms (hgef_fstream.cu, hgef_ring.cu, hgef_fused.cu): only when asked for
+  if (vec4 && (flags & HG_FORCE_FSTREAM) && fstream_available(plan, F, true)) return launch_fstream(plan, pa, s);
+  if (vec4 && (flags & HG_FORCE_RING) && ring_available(plan, F, true)) return launch_ring(plan, pa, s);
+  if (vec && (flags & HG_FORCE_PULL) && pull_available(plan, F, true)) {
     plan->kernels_launched += 2 + (plan->nheavy_segs > 0 ? 1 : 0);
     return launch_pull_any(plan, pa, s);
   }
-  const bool fused = vec && !(flags & (HG_ACCUMULATE | HG_TWO_PASS)) && fused_available(plan, F, (flags & HG_FORCE_FUSED) != 0);
+#endif
+  // stream form: both stages as lean register-only row streams, two launches, the hyperedge features make one
+  // round trip through the L2 / HBM (hgef_stream.cu): the form chosen when Y exceeds the L2
+  if (vec4 && (plain || (flags & HG_FORCE_STREAM)) && !(flags & (HG_ACCUMULATE | HG_TWO_PASS)) &&
+      stream_available(plan, F, (flags & HG_FORCE_STREAM) != 0))
+    return launch_stream(plan, pa, s);
+  // a feature length that is not a multiple of 4 on a graph that large: the same kernels on rows padded to the
+  // next multiple of 4 (one extra pass over X and Y) instead of scalar atomics over a zero-filled Y
+  if (F % 4 != 0 && plain && !(flags & HG_FORCE_SCALAR) && stream_available(plan, (F + 3) / 4 * 4, false))
+    return launch_stream_padded(plan, pa, s);
+#ifdef HGEF_LAB
+  const bool fused = vec && (flags & HG_FORCE_FUSED) && !(flags & HG_ACCUMULATE) && fused_available(plan, F, true);
+#else
+  const bool fused = false;
+#endif
+  // two-pass form: memset + one warp per balancer segment with vector reductions (small graphs: Y is L2-resident)
   if (!fused && !(flags & HG_ACCUMULATE))
     HG_CUDA_TRY(cudaMemsetAsync(d_Y, 0, (size_t)plan->num_nodes * F * sizeof(float), s));
   const bool heavy = plan->nheavy_segs > 0;
   if (heavy) {
     const size_t need = (size_t)plan->nheavy_edges * F;
-    if (need > plan->scratch_floats) {
-      HG_CUDA_TRY(cudaStreamSynchronize(s));
-      cudaFree(plan->scratch);
-      plan->scratch = nullptr;
-      plan->scratch_floats = 0;
-      if (cudaMalloc((void **)&plan->scratch, need * sizeof(float)) != cudaSuccess) {
-        cudaGetLastError();
-        return set_error(HG_ENOMEM, "aggr_forward: cannot allocate %zu bytes of scratch",
-                         need * sizeof(float));
-      }
-      plan->scratch_floats = need;
-    }
+    if (int rc = plan_grow(plan, &plan->scratch, &plan->scratch_floats, need, s, "heavy-hyperedge scratch")) return rc;
     HG_CUDA_TRY(cudaMemsetAsync(plan->scratch, 0, need * sizeof(float), s));
   }
   Args a{};
@@ -303,7 +311,9 @@ int hg_aggr_forward(hgPlan *plan, const float *d_X, const float *d_s1, const flo
   a.X = d_X; a.s1 = d_s1; a.s2 = d_s2; a.a_out = d_a_out; a.a_in = d_a_in; a.Y = d_Y;
   a.scratch = plan->scratch; a.F = F; a.lpr = lanes_per_row(F);
   plan->kernels_launched += 1 + (plan->nheavy_segs > 0 ? 1 : 0);
+#ifdef HGEF_LAB
   if (fused) return launch_fused(plan, a, s);
+#endif
   a.nwork = plan->nseg;
   unsigned grid = grid_for(plan->nseg, plan->sm_count, 8);
   if (vec) HG_DISPATCH_VPL(F, seg_pass1_kernel, grid, s, a);

@@ -1046,20 +1046,7 @@ bool pull_available(const hgPlan *plan, int F, bool force) {
   return (double)plan->nnz / (double)plan->nseg <= 0.125 * kIdxCap;
 }
 
-int ensure_xe(hgPlan *plan, int F, cudaStream_t s) {
-  const size_t need = (size_t)plan->num_edges * F;
-  if (need <= plan->xe_floats) return HG_OK;
-  HG_CUDA_TRY(cudaStreamSynchronize(s));
-  cudaFree(plan->xe);
-  plan->xe = nullptr;
-  plan->xe_floats = 0;
-  if (cudaMalloc((void **)&plan->xe, need * sizeof(float)) != cudaSuccess) {
-    cudaGetLastError();
-    return set_error(HG_ENOMEM, "aggr_forward: cannot allocate %zu bytes for the hyperedge features", need * sizeof(float));
-  }
-  plan->xe_floats = need;
-  return HG_OK;
-}
+int ensure_xe(hgPlan *plan, int F, cudaStream_t s);
 
 int launch_pull_any(hgPlan *plan, const dev::Args &base, cudaStream_t s) {
   if (int rc = ensure_xe(plan, base.F, s)) return rc;

@@ -205,6 +205,7 @@ int inclusive_sum(In in, Out out, int64_t n, cudaStream_t s) {
 int inclusive_sum_i32(const int32_t *in, int32_t *out, int64_t n, cudaStream_t s);
 
 // first-touch / single-writer flags for the fused kernel (vertex ids must fit 30 bits)
+#ifdef HGEF_LAB
 int build_fused(hgPlan *p, cudaStream_t s) {
   const int64_t N = p->num_nodes, Z = p->nnz;
   if (N >= (int64_t(1) << 30) || Z == 0 || N == 0) return HG_OK;  // cflag stays NULL: two-pass path
@@ -235,6 +236,8 @@ int build_fused(hgPlan *p, cudaStream_t s) {
   HG_CUDA_TRY(cudaStreamSynchronize(s));
   return HG_OK;
 }
+
+#endif  // HGEF_LAB
 
 // H (vertex -> hyperedges, ascending) by transposing the caller's H^T with the CSR builder
 int build_pull(hgPlan *p, cudaStream_t s) {
@@ -349,7 +352,17 @@ int build(hgPlan *p, cudaStream_t s) {
     HG_CUDA_TRY(cudaGetLastError());
     HG_CUDA_TRY(cudaStreamSynchronize(s));
   }
+  // the optional forms need segments that tile [0, nnz) exactly (the balancer's do; caller-built canonical
+  // group arrays need not): otherwise only the two-pass form is available
+  {
+    int32_t k0 = -1, kS = -1;
+    HG_CUDA_TRY(cudaMemcpy(&k0, p->key, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    HG_CUDA_TRY(cudaMemcpy(&kS, p->key + S, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (k0 != 0 || kS != p->nnz) return HG_OK;
+  }
+#ifdef HGEF_LAB
   if (int rc = build_fused(p, s)) return rc;
+#endif
   if (int rc = build_pull(p, s)) return rc;
   return build_stream(p, s);
 }
@@ -362,6 +375,25 @@ int inclusive_sum_i32(const int32_t *in, int32_t *out, int64_t n, cudaStream_t s
 }  // namespace hg
 
 using namespace hg;
+
+namespace hg {
+int plan_grow(hgPlan *p, float **buf, size_t *cap, size_t need, cudaStream_t s, const char *what) {
+  if (need <= *cap) return HG_OK;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone)
+    return set_error(HG_EINVAL, "the plan's %s buffer must grow to %zu bytes, which cannot happen while the stream is "
+                     "being captured: call hg_plan_reserve (or run the op once eagerly) first", what, need * sizeof(float));
+  float *nb = nullptr;
+  if (cudaMalloc((void **)&nb, need * sizeof(float)) != cudaSuccess) {
+    cudaGetLastError();
+    return set_error(HG_ENOMEM, "cannot allocate %zu bytes for the plan's %s", need * sizeof(float), what);
+  }
+  if (*buf) p->retired.push_back(*buf);
+  *buf = nb;
+  *cap = need;
+  return HG_OK;
+}
+}  // namespace hg
 
 extern "C" {
 
@@ -406,8 +438,13 @@ int hg_plan_destroy(hgPlan *p) {
   cudaFree(p->iso_list);
   cudaFree(p->ctrl);
   cudaFree(p->scratch);
+  cudaFree(p->pad_x);
+  cudaFree(p->pad_y);
+  for (void *q : p->retired) cudaFree(q);
   stream_free(p);
+#ifdef HGEF_LAB
   ring_free(p);
+#endif
   delete p;
   return HG_OK;
 }

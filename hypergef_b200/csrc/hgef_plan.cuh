@@ -1,6 +1,8 @@
 // hgef_plan.cuh -- the aggregation plan (internal layout; opaque in the C-ABI).
 #pragma once
 
+#include <vector>
+
 #include "hgef_common.cuh"
 
 struct hgPlan {
@@ -35,18 +37,9 @@ struct hgPlan {
   int32_t *st_ptrB = nullptr;     // [N + 1] first stage-B position of every unit (vertex in st_perm order)
   int32_t *st_perm = nullptr;     // [N] vertices ordered by their last hyperedge; the tail holds the isolated ones
   int32_t *st_ctrl = nullptr;     // ticket counters of the two-launch form
-  int32_t *st_last_ctrl = nullptr;
   int64_t st_nrunA = 0, st_nrunB = 0, st_nunitB = 0, st_niso = 0;
   int32_t st_ready = 0;
-  struct StreamSched {            // fused ticket order for one item size / lag
-    int bpi, lag, nslab;
-    int32_t GA, GB, nblk;
-    int2 *sched;
-    int32_t *ctrl;
-  };
   static constexpr int kMaxSched = 8;
-  StreamSched st_sched[kMaxSched];
-  int st_nsched = 0;
   // ring form (hgef_ring.cu): hyperedges ordered by their last stage-B read position (the discard order), and
   // merged A / B / discard ticket orders for one item size and pair of lags
   int32_t *rg_dperm = nullptr, *rg_dlast = nullptr;
@@ -66,6 +59,18 @@ struct hgPlan {
   // scratch: partial hyperedge features of heavy hyperedges, [nheavy_edges, F]; L2-resident
   float *scratch = nullptr;
   size_t scratch_floats = 0;
+  // padded copies of X / Y for feature lengths that are not a multiple of 4 (stream form on padded rows)
+  float *pad_x = nullptr, *pad_y = nullptr;
+  size_t pad_x_floats = 0, pad_y_floats = 0;
+  // buffers replaced by larger ones: a launch in flight or a captured CUDA graph may still name them, so they
+  // live until the plan is destroyed
+  std::vector<void *> retired;
   int sm_count = 148;
   int64_t kernels_launched = 0;   // this library's own kernels launched through the plan (bench.py reports it)
 };
+
+namespace hg {
+// Grows a plan-owned device buffer to `need` floats.  Never frees the old buffer before the plan dies and never
+// allocates while `s` is being captured (HG_EINVAL: reserve with hg_plan_reserve or one eager call first).
+int plan_grow(hgPlan *p, float **buf, size_t *cap, size_t need, cudaStream_t s, const char *what);
+}  // namespace hg

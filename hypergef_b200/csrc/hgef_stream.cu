@@ -1,5 +1,5 @@
 // hgef_stream.cu -- the STREAM form of the fused aggregation: both stages as lean, register-only row streams
-// (the default for graphs whose Y exceeds the L2); optionally in ONE persistent launch.
+// (the default for graphs whose Y exceeds the L2).
 //
 // What the profiles of the earlier forms said (profiles/r01_ncu_prof_r1_pull_f128.txt): the gather-only
 // two-phase form has ideal DRAM traffic but spends ~45 warp instructions per gathered row (tile staging in
@@ -21,12 +21,9 @@
 // What bounds it: DRAM at >= 1 KB rows (94-96 % of the copy peak, 1.3x the algorithmic
 // traffic because Xe makes a round trip); below that, how much the L2 serves at 24-32 warps per SM.
 //
-// FUSED launch (STAGE = -1, HGEF_ST_FUSED=1; measured slower, kept for A/B): both stages are cut into items
-// and merged into one ticket sequence in which a B item follows the A items it needs (plus a lag); warps claim
-// tickets in order, A items publish per-block completion counts (release), B items wait on a monotone
-// per-warp watermark.  Deadlock-free: an item is only claimed by a running warp, tickets are claimed in
-// order, a B item waits only for A items with smaller tickets, A items never wait; waits are bounded
-// (give-up flag -> hg_plan_check).  Wide rows (> 512 floats) are processed as column SLABS.
+// One launch per stage.  (Merging both stages into one persistent launch so that Xe is handed over inside the L2
+// was built four ways this round -- hgef_fstream.cu, hgef_ring.cu, lab library -- and is slower: DESIGN.md
+// section 4.)  Wide rows (> 512 floats) are processed as column SLABS.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -46,7 +43,6 @@ struct StreamArgs {
   float *out[2];
   const float *w_in[2], *w_o1[2], *w_o2[2];  // gather-side weight per source row; output scales per output row
   int32_t nrun0[2];                          // base runs
-  const int2 *sched;                         // fused: {item << 1 | stage, #completion blocks needed}
   int32_t *ctrl;
   const int32_t *iso;                        // vertices in no hyperedge: Y row = 0
   int32_t niso;
@@ -54,31 +50,12 @@ struct StreamArgs {
   int32_t nslab, slabF;                      // column slabs of slabF floats
   int32_t F;                                 // row stride (floats)
   int32_t k0;                                // base runs per sub-warp run
-  int32_t stage;                             // unfused: the stage this launch runs
-  int32_t nblk, GA;                          // fused: completion blocks per slab, A items
+  int32_t stage;                             // the stage this launch runs
   int32_t y_stream;                          // stage-B output stores carry the streaming (evict-first) hint
-  int32_t batch;                             // tickets claimed per atomic (two-launch form)
+  int32_t pdl;                               // stage B is a programmatic dependent launch of stage A
 };
 
-__device__ __forceinline__ int ld_relaxed_i32(const int *p) {
-  int v;
-  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void red_inc_relaxed(int *p) {
-  asm volatile("red.relaxed.gpu.global.add.s32 [%0], 1;" ::"l"(p) : "memory");
-}
-// row loads.  Fused launches read rows written earlier in the SAME launch: L2-coherent loads
-// (no L1 allocation), volatile so that they stay behind the acquire fence of the wait.
-template <bool CG>
-__device__ __forceinline__ float4 ld_row16(const float *p) {
-  if (CG) {
-    float4 v;
-    asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
-  }
-  return __ldg(reinterpret_cast<const float4 *>(p));
-}
+__device__ __forceinline__ float4 ld_row16(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
 __device__ __forceinline__ void st_row16(float *p, float4 v) {
   asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
@@ -95,15 +72,13 @@ struct SGeo {
   static constexpr int kStride = SW * 4;                        // floats between a lane's vectors
 };
 
-// STAGE 0 / 1: the launch runs one stage (its arrays are addressed straight from the constant bank);
-// STAGE -1: fused launch, the stage comes with the ticket.
+// STAGE 0 / 1: the stage this launch runs (its arrays are addressed straight from the constant bank).
 // PIPE: rows are loaded in half-batches into two alternating register sets (half h + 1 is issued before half
 // h is consumed); otherwise whole batches are loaded and then consumed (better for the widest rows, where
 // a half-batch is a single 2 KB row).
 template <int SW, int VPL, bool HAS_WIN, int STAGE, int MINB, bool PIPE>
 __global__ void __launch_bounds__(kThreads, MINB) stream_kernel(const StreamArgs sa) {
   using G = SGeo<SW, VPL>;
-  constexpr bool FUSED = STAGE < 0;
   constexpr int HB = PIPE ? G::kHB : G::kU, NH = SW / HB;
   static_assert(!PIPE || (NH >= 2 && NH % 2 == 0), "a chunk is a whole number of half-batch pairs");
   const int lane = threadIdx.x & 31;
@@ -112,33 +87,27 @@ __global__ void __launch_bounds__(kThreads, MINB) stream_kernel(const StreamArgs
   const int F = sa.F;
   const uint32_t row_bytes = (uint32_t)F * 4u;
   const int total = sa.nitem * sa.nslab;
-  int blk_wm = 0, wm_slab = 0;
   uint32_t pat = 0;   // bit (stream * SW) for every row stream of the warp
 #pragma unroll
   for (int q = 0; q < G::kSub; ++q) pat |= 1u << (q * SW);
 
-  int t_next = 0, t_left = 0;
+  if (sa.pdl) {
+    // stage A lets its dependent (stage B) be scheduled as soon as every A CTA has started; stage B must not
+    // touch Xe before stage A's memory operations are complete and flushed
+    if (STAGE == 0) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    else asm volatile("griddepcontrol.wait;" ::: "memory");
+  }
   for (;;) {
-    if (t_left == 0) {   // tickets are claimed `batch` at a time (the counter is one address for the whole grid)
-      int tb = 0;
-      if (lane == 0) tb = atomicAdd(sa.ctrl, sa.batch);
-      t_next = __shfl_sync(kFull, tb, 0);
-      t_left = sa.batch;
-    }
-    const int t = t_next++;
-    --t_left;
+    int t = 0;
+    if (lane == 0) t = atomicAdd(sa.ctrl, 1);
+    t = __shfl_sync(kFull, t, 0);
     if (t >= total) break;
     const int slab = sa.nslab > 1 ? t / sa.nitem : 0;
     const int k = t - slab * sa.nitem;
     const int col0 = slab * sa.slabF;
     const int Fs = min(sa.slabF, F - col0);
-    int stage = FUSED ? 0 : STAGE, gid = k, need = 0;
-    if (FUSED) {
-      const int2 s = __ldg(sa.sched + k);
-      stage = s.x & 1;
-      gid = s.x >> 1;
-      need = s.y;
-    }
+    constexpr int stage = STAGE;
+    const int gid = k;
     const float *in = sa.in[stage] + col0;
     float *out = sa.out[stage] + col0;
     // column mask of this lane's vectors; a masked vector LOADS column 0 of the slab instead (no branch
@@ -154,7 +123,7 @@ __global__ void __launch_bounds__(kThreads, MINB) stream_kernel(const StreamArgs
     }
 
     // this ticket's share of the vertices that no hyperedge touches (only the B side has any)
-    if (sa.niso > 0 && (FUSED || STAGE == 1)) {
+    if (sa.niso > 0 && STAGE == 1) {
       const int i0 = (int)((int64_t)sa.niso * k / sa.nitem), i1 = (int)((int64_t)sa.niso * (k + 1) / sa.nitem);
       for (int i = i0 + sub; i < i1; i += G::kSub) {
         float *yp = sa.out[1] + (int64_t)__ldg(sa.iso + i) * F + col0;
@@ -173,32 +142,6 @@ __global__ void __launch_bounds__(kThreads, MINB) stream_kernel(const StreamArgs
     const int64_t r0 = ((int64_t)gid * G::kSub + sub) * sa.k0;
     const int32_t ps = __ldg(sa.run[stage] + min(r0, (int64_t)nrun0));
     const int32_t pe = __ldg(sa.run[stage] + min(r0 + sa.k0, (int64_t)nrun0));
-
-    if (FUSED && stage == 1 && need > 0) {
-      // all A items of completion blocks [0, need) of this slab must be published
-      if (slab != wm_slab) { wm_slab = slab; blk_wm = 0; }
-      if (blk_wm < need) {
-        const int *cnt = sa.ctrl + kCtrlHdr + (int64_t)slab * sa.nblk;
-        unsigned spins = 0;
-        while (blk_wm < need) {
-          const int b = blk_wm + lane;
-          bool done = true;
-          if (b < need) done = ld_relaxed_i32(cnt + b) == min(kBlk, sa.GA - b * kBlk);
-          const unsigned m = __ballot_sync(kFull, done);
-          blk_wm = min(need, blk_wm + (m == kFull ? 32 : __ffs(~m) - 1));
-          if (blk_wm < need && m != kFull) {
-            __nanosleep(64);
-            // bounded: a protocol bug must not hang the GPU; once one item gave up, nobody waits any more
-            ++spins;
-            if (spins > (1u << 20) || ((spins & 255u) == 0 && ld_relaxed_i32(sa.ctrl + 1) != 0)) {
-              if (lane == 0) atomicExch(sa.ctrl + 1, 1);
-              break;
-            }
-          }
-        }
-        asm volatile("fence.acq_rel.gpu;" ::: "memory");
-      }
-    }
 
     // ---- stream the run.  Chunks of SW positions: their src / dst words one per lane, handed out by
     // shuffles.  Rows are loaded in half-batches of HB rows into two alternating register sets: half
@@ -221,7 +164,7 @@ __global__ void __launch_bounds__(kThreads, MINB) stream_kernel(const StreamArgs
         const uint32_t id = __shfl_sync(kFull, words, j0 + u, SW);
         const uint64_t rb = (uint64_t)id * row_bytes;   // one IMAD.WIDE.U32 per vector below
 #pragma unroll
-        for (int v = 0; v < VPL; ++v) x[u][v] = ld_row16<FUSED>(reinterpret_cast<const float *>(in_v[v] + rb));
+        for (int v = 0; v < VPL; ++v) x[u][v] = ld_row16(reinterpret_cast<const float *>(in_v[v] + rb));
       }
     };
     if (PIPE) load_half(x0, c_src, 0);
@@ -306,13 +249,6 @@ __global__ void __launch_bounds__(kThreads, MINB) stream_kernel(const StreamArgs
       c_dst = n_dst;
     }
 
-    if (FUSED && stage == 0) {   // publish: this item's Xe rows are complete
-      __syncwarp();
-      if (lane == 0) {
-        asm volatile("fence.acq_rel.gpu;" ::: "memory");
-        red_inc_relaxed(sa.ctrl + kCtrlHdr + (int64_t)slab * sa.nblk + gid / kBlk);
-      }
-    }
   }
 }
 
@@ -392,51 +328,6 @@ __global__ void count_units_kernel(int64_t n, const int32_t *__restrict__ keys_s
   if (i < n && keys_sorted[i] < m && (i + 1 == n || keys_sorted[i + 1] >= m)) *out = (int32_t)(i + 1);
 }
 
-// ---- fused schedule for one (items of `bpi` base runs, lag) configuration ----
-// a_after[gb] = number of A items that precede B item gb in the ticket order
-__global__ void sched_b_kernel(int32_t GB, int32_t GA, int32_t bpi, int32_t lag, const int32_t *__restrict__ runA,
-                               int32_t nrunA, const int32_t *__restrict__ runB, int32_t nrunB,
-                               const int32_t *__restrict__ needB, int32_t *__restrict__ a_after,
-                               int32_t *__restrict__ need_blk) {
-  const int32_t gb = blockIdx.x * blockDim.x + threadIdx.x;
-  if (gb >= GB) return;
-  const int32_t p0 = runB[min((int64_t)gb * bpi, (int64_t)nrunB)], p1 = runB[min(((int64_t)gb + 1) * bpi, (int64_t)nrunB)];
-  (void)p0;
-  int32_t cnt = 0;   // A items [0, cnt) must be complete
-  // An item can be empty (a unit longer than an item spills over the following ones).  The need is taken
-  // from the last position at or before the item's end in every case, so that it is monotone in gb --
-  // the merge below relies on that.
-  if (p1 > 0) {
-    const int32_t npos = needB[p1 - 1];   // stage-A positions [0, npos) must be complete
-    if (npos > 0) {
-      int32_t lo = 0, hi = GA;   // first A item whose end position >= npos
-      while (lo < hi) {
-        const int32_t mid = (lo + hi) >> 1;
-        const int32_t endp = runA[min(((int64_t)mid + 1) * bpi, (int64_t)nrunA)];
-        if (endp < npos) lo = mid + 1; else hi = mid;
-      }
-      cnt = min(lo + 1, GA);
-    }
-  }
-  const int32_t nb = (cnt + kBlk - 1) / kBlk;
-  need_blk[gb] = nb;
-  a_after[gb] = cnt == 0 ? 0 : min(GA, nb * kBlk + lag);
-}
-
-__global__ void sched_merge_kernel(int32_t GA, int32_t GB, const int32_t *__restrict__ a_after,
-                                   const int32_t *__restrict__ need_blk, int2 *__restrict__ sched) {
-  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < GB) sched[i + a_after[i]] = make_int2((i << 1) | 1, need_blk[i]);
-  if (i < GA) {   // B items with a_after <= i come first
-    int32_t lo = 0, hi = GB;
-    while (lo < hi) {
-      const int32_t mid = (lo + hi) >> 1;
-      if (a_after[mid] <= i) lo = mid + 1; else hi = mid;
-    }
-    sched[i + lo] = make_int2(i << 1, 0);
-  }
-}
-
 __global__ void zero_rows_kernel(int64_t nrows, const int32_t *__restrict__ segs, const int32_t *__restrict__ seg_edge,
                                  float *__restrict__ xe, int F) {
   const int lane = threadIdx.x & 31;
@@ -455,19 +346,12 @@ int dev_alloc(T **p, size_t n) {
   return HG_OK;
 }
 
-int env_int(const char *name, int dflt) {
-  const char *v = getenv(name);
-  return v && *v ? atoi(v) : dflt;
-}
-
 }  // namespace
 
 void stream_free(hgPlan *p) {
   cudaFree(p->st_srcA); cudaFree(p->st_dstA); cudaFree(p->st_runA);
   cudaFree(p->st_srcB); cudaFree(p->st_dstB); cudaFree(p->st_needB); cudaFree(p->st_runB);
   cudaFree(p->st_perm); cudaFree(p->st_ctrl); cudaFree(p->st_ptrB);
-  for (int i = 0; i < p->st_nsched; ++i) { cudaFree(p->st_sched[i].sched); cudaFree(p->st_sched[i].ctrl); }
-  p->st_nsched = 0;
 }
 
 // Builds the two row programs.  Needs the canonical segment schedule and H (build_pull).
@@ -541,6 +425,7 @@ int build_stream(hgPlan *p, cudaStream_t s) {
   p->st_nrunB = ceil_div<int64_t>(Z, kL0);
   if (int rc = dev_alloc(&p->st_runB, p->st_nrunB + 1)) return rc;
   if (int rc = dev_alloc(&p->st_ctrl, 2 * kCtrlHdr)) return rc;
+  HG_CUDA_TRY(cudaMemsetAsync(p->st_ctrl, 0, 2 * kCtrlHdr * sizeof(int32_t), s));   // the launches reset it themselves
   const int64_t NB = p->st_nunitB;
   if (NB > 0)
     prog_fill_kernel<<<(unsigned)ceil_div<int64_t>(NB * 32, 256), 256, 0, s>>>(
@@ -566,41 +451,9 @@ int stream_build_runs(hgPlan *p, int L0, int32_t **runA, int64_t *nrunA, int32_t
 
 namespace {
 
-// schedule (and control words) for items of `bpi` base runs; cached in the plan
-int get_sched(hgPlan *p, int bpi, int lag, int nslab, cudaStream_t s, hgPlan::StreamSched **out) {
-  for (int i = 0; i < p->st_nsched; ++i) {
-    hgPlan::StreamSched &c = p->st_sched[i];
-    if (c.bpi == bpi && c.lag == lag && c.nslab >= nslab) { *out = &c; return HG_OK; }
-  }
-  if (p->st_nsched == hgPlan::kMaxSched) {   // recycle the oldest entry
-    HG_CUDA_TRY(cudaStreamSynchronize(s));
-    cudaFree(p->st_sched[0].sched); cudaFree(p->st_sched[0].ctrl);
-    for (int i = 1; i < p->st_nsched; ++i) p->st_sched[i - 1] = p->st_sched[i];
-    --p->st_nsched;
-  }
-  hgPlan::StreamSched c{};
-  c.bpi = bpi; c.lag = lag; c.nslab = nslab;
-  c.GA = (int32_t)ceil_div<int64_t>(p->st_nrunA, bpi);
-  c.GB = (int32_t)ceil_div<int64_t>(p->st_nrunB, bpi);
-  c.nblk = (c.GA + kBlk - 1) / kBlk;
-  if (int rc = dev_alloc(&c.sched, (size_t)c.GA + c.GB)) return rc;
-  if (int rc = dev_alloc(&c.ctrl, (size_t)kCtrlHdr + (size_t)c.nblk * nslab)) return rc;
-  DevBuf<int32_t> a_after, need_blk;
-  HG_CUDA_TRY(a_after.alloc(c.GB)); HG_CUDA_TRY(need_blk.alloc(c.GB));
-  sched_b_kernel<<<GRID(c.GB), 0, s>>>(c.GB, c.GA, bpi, lag, p->st_runA, (int32_t)p->st_nrunA, p->st_runB,
-                                      (int32_t)p->st_nrunB, p->st_needB, a_after.p, need_blk.p);
-  const int32_t gmax = c.GA > c.GB ? c.GA : c.GB;
-  sched_merge_kernel<<<GRID(gmax), 0, s>>>(c.GA, c.GB, a_after.p, need_blk.p, c.sched);
-  HG_CUDA_TRY(cudaGetLastError());
-  HG_CUDA_TRY(cudaStreamSynchronize(s));
-  p->st_sched[p->st_nsched] = c;
-  *out = &p->st_sched[p->st_nsched++];
-  return HG_OK;
-}
-
 struct StreamCfg {
-  int sw, vpl, slabF, nslab, k0, ctas, lag, occ;
-  bool fused, pipe;
+  int sw, vpl, slabF, nslab, k0, ctas, occ;
+  bool pipe, pdl;
 };
 
 template <int SW, int VPL, bool HAS_WIN, int STAGE>
@@ -615,17 +468,22 @@ int launch_one(hgPlan *p, StreamArgs &sa, const StreamCfg &cfg, cudaStream_t s) 
   const int64_t useful = ceil_div<int64_t>((int64_t)sa.nitem * sa.nslab, kWarpsPerBlock);
   if (grid > useful) grid = useful;
   if (grid < 1) grid = 1;
-  kern<<<(unsigned)grid, kThreads, 0, s>>>(sa);
-  HG_CUDA_TRY(cudaGetLastError());
+  cudaLaunchConfig_t lc{};
+  lc.gridDim = dim3((unsigned)grid);
+  lc.blockDim = dim3(kThreads);
+  lc.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = attr;
+  lc.numAttrs = (STAGE == 1 && sa.pdl) ? 1 : 0;
+  HG_CUDA_TRY(cudaLaunchKernelEx(&lc, kern, sa));
   return HG_OK;
 }
 
-// stage: 0 / 1 = one stage per launch, -1 = fused
 int dispatch(hgPlan *p, StreamArgs &sa, const StreamCfg &cfg, int stage, bool has_win, cudaStream_t s) {
 #define HG_CASE(SW_, VPL_)                                                                             \
   if (cfg.sw == SW_ && cfg.vpl == VPL_) {                                                              \
-    if (stage < 0)                                                                                     \
-      return has_win ? launch_one<SW_, VPL_, true, -1>(p, sa, cfg, s) : launch_one<SW_, VPL_, false, -1>(p, sa, cfg, s); \
     if (stage == 1) return launch_one<SW_, VPL_, false, 1>(p, sa, cfg, s);                             \
     return has_win ? launch_one<SW_, VPL_, true, 0>(p, sa, cfg, s) : launch_one<SW_, VPL_, false, 0>(p, sa, cfg, s);    \
   }
@@ -640,19 +498,24 @@ int dispatch(hgPlan *p, StreamArgs &sa, const StreamCfg &cfg, int stage, bool ha
 bool stream_available(const hgPlan *plan, int F, bool force) {
   if (!plan->st_ready) return false;
   if (force) return true;
-  static const int off = env_int("HGEF_NO_STREAM", 0);
-  if (off) return false;
+  if (tune_get("stream", 1) == 0) return false;
   // below ~64 MB of Y the two-pass form (everything L2-resident, one warp per segment) has the lower latency
-  if ((double)plan->num_nodes * F * 4.0 < 64.0 * 1048576.0) return false;
+  if ((double)plan->num_nodes * F * 4.0 < (double)tune_get("stream_min_mb", 64) * 1048576.0) return false;
   return plan->max_vdeg <= 65536;   // one sub-warp walks a vertex's hyperedges
 }
 
+int ensure_xe(hgPlan *plan, int F, cudaStream_t s) {
+  return plan_grow(plan, &plan->xe, &plan->xe_floats, (size_t)plan->num_edges * F, s, "hyperedge features");
+}
+
+// Launch geometry.  Defaults from the sweeps in profiles/; every one can be overridden through hg_tune_set
+// (st_slab, st_sw, st_l, st_ctas, st_occ, st_pipe, st_cs, st_pdl, st_only) -- read from a table, not the environment.
 int launch_stream(hgPlan *p, const dev::Args &a, cudaStream_t s) {
   const int F = a.F;
   if (int rc = ensure_xe(p, F, s)) return rc;
   StreamCfg cfg{};
   // geometry: SW lanes x VPL 128-bit vectors per row slab
-  int slabF = env_int("HGEF_ST_SLAB", 0);
+  int slabF = tune_get("st_slab", 0);
   if (slabF <= 0) slabF = F <= 512 ? F : 512;
   if (slabF > 512) slabF = 512;
   slabF = (slabF + 3) / 4 * 4;
@@ -660,26 +523,25 @@ int launch_stream(hgPlan *p, const dev::Args &a, cudaStream_t s) {
   cfg.slabF = slabF;
   cfg.nslab = (F + slabF - 1) / slabF;
   cfg.sw = slabF <= 16 ? 4 : (slabF <= 32 ? 8 : (slabF <= 64 ? 16 : 32));
-  {   // HGEF_ST_SW: lanes per row (the lane then holds 1, 2 or 4 vectors of the row)
-    const int sw_env = env_int("HGEF_ST_SW", 0);
-    if (sw_env == 4 || sw_env == 8 || sw_env == 16 || sw_env == 32) cfg.sw = sw_env;
+  {   // st_sw: lanes per row (the lane then holds 1, 2 or 4 vectors of the row)
+    const int sw_t = tune_get("st_sw", 0);
+    if (sw_t == 4 || sw_t == 8 || sw_t == 16 || sw_t == 32) cfg.sw = sw_t;
     while (cfg.sw < 32 && slabF > cfg.sw * 16) cfg.sw *= 2;
   }
   cfg.vpl = slabF <= cfg.sw * 4 ? 1 : (slabF <= cfg.sw * 8 ? 2 : 4);
   const int ksub = 32 / cfg.sw;
   // run length per row stream: ~32 KB of gathered rows per warp item by default
-  int L = env_int("HGEF_ST_L", 0);
+  int L = tune_get("st_l", 0);
   if (L <= 0) {
     L = (32 * 1024) / (slabF * 4 * ksub);
     if (L < kL0) L = kL0;
     if (L > 256) L = 256;
   }
   cfg.k0 = (L + kL0 - 1) / kL0;
-  cfg.ctas = env_int("HGEF_ST_CTAS", 0);
-  cfg.occ = env_int("HGEF_ST_OCC", 3);
-  cfg.pipe = env_int("HGEF_ST_PIPE", cfg.vpl < 4 ? 1 : 0) != 0;
-  cfg.fused = env_int("HGEF_ST_FUSED", 0) != 0;
-  cfg.lag = env_int("HGEF_ST_LAG", -1);
+  cfg.ctas = tune_get("st_ctas", 0);
+  cfg.occ = tune_get("st_occ", 3);
+  cfg.pipe = tune_get("st_pipe", cfg.vpl < 4 ? 1 : 0) != 0;
+  cfg.pdl = tune_get("st_pdl", 1) != 0;
   const int bpi = cfg.k0 * ksub;
   const bool has_win = a.a_in != nullptr;
 
@@ -696,43 +558,56 @@ int launch_stream(hgPlan *p, const dev::Args &a, cudaStream_t s) {
   sa.in[1] = p->xe; sa.out[1] = a.Y; sa.w_in[1] = nullptr; sa.w_o1[1] = a.a_out; sa.w_o2[1] = nullptr;
   sa.iso = p->st_perm + p->st_nunitB; sa.niso = (int32_t)p->st_niso;
   sa.nslab = cfg.nslab; sa.slabF = cfg.slabF; sa.F = F; sa.k0 = cfg.k0;
-  sa.y_stream = env_int("HGEF_ST_CS", 1);
-  sa.batch = cfg.fused ? 1 : tune_get("st_batch", 1);
-  if (sa.batch < 1) sa.batch = 1;
+  sa.y_stream = tune_get("st_cs", 1);
   const int32_t GA = (int32_t)ceil_div<int64_t>(p->st_nrunA, bpi), GB = (int32_t)ceil_div<int64_t>(p->st_nrunB, bpi);
 
-  if (cfg.fused) {
-    if (cfg.lag < 0) cfg.lag = 2 * kBlk;
-    hgPlan::StreamSched *sc = nullptr;
-    if (int rc = get_sched(p, bpi, cfg.lag, cfg.nslab, s, &sc)) return rc;
-    HG_CUDA_TRY(cudaMemsetAsync(sc->ctrl, 0, ((size_t)kCtrlHdr + (size_t)sc->nblk * cfg.nslab) * sizeof(int32_t), s));
-    sa.sched = sc->sched; sa.ctrl = sc->ctrl; sa.nitem = sc->GA + sc->GB; sa.nblk = sc->nblk; sa.GA = sc->GA;
-    p->st_last_ctrl = sc->ctrl;
-    ++p->kernels_launched;
-    return dispatch(p, sa, cfg, -1, has_win, s);
-  }
-  // two launches, each stage its own ticket counter
-  HG_CUDA_TRY(cudaMemsetAsync(p->st_ctrl, 0, 2 * kCtrlHdr * sizeof(int32_t), s));
-  const int only = env_int("HGEF_ST_ONLY", 0);   // timing: 1 = stage A, 2 = stage B
+  // two launches, each stage its own ticket counter; the counters reset themselves (the last warp to leave a
+  // launch zeroes its counter), so a call is exactly two kernel launches and stage B can be a programmatic
+  // dependent launch: its CTAs are scheduled while stage A drains and wait (griddepcontrol.wait) for A's
+  // memory to be flushed before they touch Xe
+  const int only = tune_get("st_only", 0);   // timing: 1 = stage A, 2 = stage B
   if (only != 2) {
-    sa.stage = 0; sa.nitem = GA; sa.ctrl = p->st_ctrl;
+    sa.stage = 0; sa.nitem = GA; sa.ctrl = p->st_ctrl; sa.pdl = (cfg.pdl && only == 0) ? 1 : 0;
     ++p->kernels_launched;
     if (int rc = dispatch(p, sa, cfg, 0, has_win, s)) return rc;
   }
   if (only == 1) return HG_OK;
-  sa.stage = 1; sa.nitem = GB; sa.ctrl = p->st_ctrl + kCtrlHdr;
+  sa.stage = 1; sa.nitem = GB; sa.ctrl = p->st_ctrl + kCtrlHdr; sa.pdl = (cfg.pdl && only == 0) ? 1 : 0;
   ++p->kernels_launched;
   return dispatch(p, sa, cfg, 1, false, s);
 }
 
-int stream_check(hgPlan *plan, cudaStream_t s) {
-  if (!plan->st_last_ctrl) return HG_OK;
-  int32_t stalled = 0;
-  HG_CUDA_TRY(cudaMemcpyAsync(&stalled, plan->st_last_ctrl + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-  HG_CUDA_TRY(cudaStreamSynchronize(s));
-  if (stalled)
-    return set_error(HG_ECUDA, "stream aggregation: a stage-B item gave up waiting for its hyperedge features; "
-                               "the last result is invalid");
+// ---- feature lengths that are not a multiple of 4: the same kernels on rows padded to the next multiple
+namespace {
+__global__ void pad_rows_kernel(int64_t n, int F, int Fp, const float *__restrict__ in, float *__restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;   // one thread per padded element
+  if (i >= n * Fp) return;
+  const int64_t r = i / Fp;
+  const int c = (int)(i - r * Fp);
+  out[i] = c < F ? in[r * F + c] : 0.0f;
+}
+__global__ void unpad_rows_kernel(int64_t n, int F, int Fp, const float *__restrict__ in, float *__restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;   // one thread per output element
+  if (i >= n * F) return;
+  const int64_t r = i / F;
+  const int c = (int)(i - r * F);
+  out[i] = in[r * Fp + c];
+}
+}  // namespace
+
+int launch_stream_padded(hgPlan *p, const dev::Args &a, cudaStream_t s) {
+  const int F = a.F, Fp = (F + 3) / 4 * 4;
+  const int64_t N = p->num_nodes;
+  if (int rc = plan_grow(p, &p->pad_x, &p->pad_x_floats, (size_t)N * Fp, s, "padded input")) return rc;
+  if (int rc = plan_grow(p, &p->pad_y, &p->pad_y_floats, (size_t)N * Fp, s, "padded output")) return rc;
+  pad_rows_kernel<<<GRID(N * Fp), 0, s>>>(N, F, Fp, a.X, p->pad_x);
+  HG_CUDA_TRY(cudaGetLastError());
+  dev::Args b = a;
+  b.X = p->pad_x; b.Y = p->pad_y; b.F = Fp;
+  if (int rc = launch_stream(p, b, s)) return rc;
+  unpad_rows_kernel<<<GRID(N * F), 0, s>>>(N, F, Fp, p->pad_y, a.Y);
+  HG_CUDA_TRY(cudaGetLastError());
+  p->kernels_launched += 2;
   return HG_OK;
 }
 

@@ -69,13 +69,31 @@ def tune(**knobs) -> None:
 # ----------------------------------------------------------------------------
 # argument checking
 # ----------------------------------------------------------------------------
+_I32_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()   # (data_ptr, numel, version) -> (source, int32 copy)
+_I32_CACHE_SIZE = 64
+
+
 def _index(t, name):
     if not isinstance(t, torch.Tensor):
         raise TypeError(f"{name} must be a torch.Tensor")
     if not t.is_cuda:
         raise ValueError(f"{name} must be a CUDA tensor (hypergef_b200 has no CPU path)")
     if t.dtype == torch.int64:
-        t = t.to(torch.int32)
+        # int64 index tensors (accepted for large graphs) are converted ONCE: the copy is cached against the
+        # source tensor, so the plan cache (keyed on data pointers) hits on the next call instead of
+        # rebuilding the plan from a fresh copy every time
+        ident = (t.data_ptr(), t.numel(), t._version, str(t.device))
+        with _PLANS_LOCK:
+            hit = _I32_CACHE.get(ident)
+            if hit is not None:
+                _I32_CACHE.move_to_end(ident)
+                return hit[1]
+        c = t.to(torch.int32).contiguous().reshape(-1)
+        with _PLANS_LOCK:
+            _I32_CACHE[ident] = (t, c)          # holding `t` keeps its data_ptr from being recycled
+            while len(_I32_CACHE) > _I32_CACHE_SIZE:
+                _I32_CACHE.popitem(last=False)
+        return c
     if t.dtype != torch.int32:
         raise TypeError(f"{name} must be int32 (or int64), got {t.dtype}")
     return t.contiguous().reshape(-1)
@@ -141,6 +159,11 @@ class Plan:
         _native.call("hg_plan_launches", self.handle, C.byref(n))
         return n.value
 
+    def reserve(self, F_max: int) -> None:
+        """Size the plan's per-call buffers for feature lengths up to ``F_max`` (hg_plan_reserve): after this no
+        aggregation call allocates -- required before capturing calls with a new, wider F into a CUDA graph."""
+        _native.call("hg_plan_reserve", self.handle, int(F_max), torch.cuda.current_stream(self.device_index).cuda_stream)
+
     def debug_words(self):
         """The 8 control words of the last ring-form launch (hg_plan_debug; diagnostic)."""
         out = (C.c_int32 * 8)()
@@ -168,6 +191,7 @@ _PLAN_CACHE_SIZE = 16
 def clear_plan_cache() -> None:
     with _PLANS_LOCK:
         _PLANS.clear()
+        _I32_CACHE.clear()
 
 
 def get_plan(key, row, st, ed, indices_t, num_nodes, num_edges) -> Plan:
@@ -275,6 +299,14 @@ class HostPipeline:
             raise ValueError(f"X_host has {N} rows, the graph has {plan.num_nodes} vertices")
         dev = plan.device_index
         with torch.cuda.device(dev):
+            # device inputs (the scale vectors) may have been produced on the caller's stream just now: the
+            # private streams start after it, and the caching allocator is told who else uses those tensors
+            cur = torch.cuda.current_stream(dev)
+            self.h2d.wait_stream(cur)
+            self.compute.wait_stream(cur)
+            for t in (s1, s2, a_out, a_in):
+                if isinstance(t, torch.Tensor) and t.is_cuda:
+                    t.record_stream(self.compute)
             if self.col_slab <= 0:          # whole matrix, buffers from the caching allocator
                 with torch.cuda.stream(self.h2d):
                     Xd = X_host.to(plan.device, non_blocking=True)
@@ -415,27 +447,60 @@ def _dev_stream(t):
     return dev, torch.cuda.current_stream(dev).cuda_stream
 
 
+MEAN_NGS = 64          # balancer segment size of the plan built for the (un-balanced) mean / max entry points
+MEAN_BALANCED = True   # False: the reference's own one-warp-per-hyperedge scheme (hg_aggr_mean), kept for A/B
+
+
+def _csr_plan(csrptr_t, indices_t, N, M) -> Plan:
+    """Plan for an UN-balanced ``H^T`` CSR: the reference's mean / max ops take no balancer arrays
+    (hgnnaggr.cc:131-144) and walk a whole hyperedge with one warp; here the device balancer cuts the rows into
+    segments first, so a 12 345-member hyperedge is shared by many warps like in the sum op.  Cached on the CSR."""
+    from .balancer import balance_schedule
+    ident = ("csr", csrptr_t.data_ptr(), indices_t.data_ptr(), csrptr_t.numel(), indices_t.numel(), N, M, str(csrptr_t.device))
+    with _PLANS_LOCK:
+        plan = _PLANS.get(ident)
+        if plan is not None:
+            _PLANS.move_to_end(ident)
+            return plan
+    bs = balance_schedule(MEAN_NGS, csrptr_t)
+    plan = Plan(bs.balan_key, bs.balan_row, bs.group_st, bs.group_ed, indices_t, N, M)
+    plan.tensors = plan.tensors + (csrptr_t,)
+    with _PLANS_LOCK:
+        _PLANS[ident] = plan
+        while len(_PLANS) > _PLAN_CACHE_SIZE:
+            _PLANS.popitem(last=False)
+    return plan
+
+
+def _mean_scale(csrptr_t, s1):
+    """degE[e] / |e|: the mean over the members folded into the hyperedge scale (hgnnaggr_cuda.cu:107)."""
+    deg = (csrptr_t[1:] - csrptr_t[:-1]).to(torch.float32).clamp_(min=1.0)
+    return (1.0 / deg) if s1 is None else (s1 / deg)
+
+
 class _MeanF1(torch.autograd.Function):
     @staticmethod
     def forward(ctx, csrptr_t, indices_t, node_feat, degE, degV, W):
         csrptr_t, indices_t, X, s1, a_out, s2, N, M = _csr_args(csrptr_t, indices_t, node_feat, degE, degV, W)
+        ctx.args = (csrptr_t, indices_t, s1, a_out, s2, N, M)
+        return _MeanF1._apply(ctx.args, X)
+
+    @staticmethod
+    def _apply(args, X):
+        csrptr_t, indices_t, s1, a_out, s2, N, M = args
+        if MEAN_BALANCED and M > 0 and indices_t.numel() > 0:
+            # mean = sum with degE / |e| as the hyperedge scale: the balanced sum kernels do the work
+            return aggregate(_csr_plan(csrptr_t, indices_t, N, M), X, s1=_mean_scale(csrptr_t, s1), s2=s2, a_out=a_out)
         out = torch.empty_like(X)
         dev, stream = _dev_stream(X)
         _native.call("hg_aggr_mean", N, M, csrptr_t.data_ptr(), indices_t.data_ptr(), X.data_ptr(),
                      _ptr(s1), _ptr(s2), _ptr(a_out), out.data_ptr(), X.shape[1], 0, dev, stream)
-        ctx.args = (csrptr_t, indices_t, s1, a_out, s2, N, M)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
         # hgnnaggr_cuda.cu:115-142: the same mean operator applied to grad_out
-        csrptr_t, indices_t, s1, a_out, s2, N, M = ctx.args
-        G = grad_out.contiguous()
-        out = torch.empty_like(G)
-        dev, stream = _dev_stream(G)
-        _native.call("hg_aggr_mean", N, M, csrptr_t.data_ptr(), indices_t.data_ptr(), G.data_ptr(),
-                     _ptr(s1), _ptr(s2), _ptr(a_out), out.data_ptr(), G.shape[1], 0, dev, stream)
-        return None, None, out, None, None, None
+        return None, None, _MeanF1._apply(ctx.args, grad_out.contiguous()), None, None, None
 
 
 class _MaxF1(torch.autograd.Function):

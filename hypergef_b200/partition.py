@@ -167,29 +167,79 @@ class CudaBackend:
 
 class PartitionedAggregator:
     """``Y[V_r] = (diag(a_out) H diag(s1*s2) H^T diag(a_in) X)[V_r]`` with X, Y, a_* sharded by vertex
-    block and the hyperedge scales ``s1``, ``s2`` given as GLOBAL ``[M]`` arrays."""
+    block and the hyperedge scales ``s1``, ``s2`` given as GLOBAL ``[M]`` arrays.
+
+    The boundary hyperedges of this rank are re-ordered once as ``[owned | owned by rank 0 | rank 1 | ...]`` so
+    that every block of the exchange is a CONTIGUOUS slice of the partial-feature matrix ``P``: the partial rows
+    go out straight from ``P`` (no gather), the completed rows come back straight into ``P`` (no scatter), and
+    ``P`` itself is what stage 2 reads.  Per call, the only feature-wide copies left beside the two kernels and
+    the two ``all_to_all`` are the accumulation of the received partial rows into the owned rows and the gather of
+    the completed rows each peer asked for.  All exchange buffers are allocated once per feature length."""
 
     def __init__(self, info: PartitionInfo, backend, group=None):
         self.info, self.backend, self.group = info, backend, group
         self.plan = backend.prepare_interior(info.int_ptr, info.int_ind, info.num_local, info.int_edges.numel())
         dev = info.bnd_ptr.device
-        nrecv = sum(int(t.numel()) for t in info.recv_own_pos)
-        self.recv_map = torch.cat(info.recv_own_pos).to(torch.int32) if nrecv else torch.empty(0, dtype=torch.int32, device=dev)
-        self.recv_ptr = torch.arange(nrecv + 1, dtype=torch.int32, device=dev)
-        self.send_cat = torch.cat(info.send_rows) if info.world > 1 else torch.empty(0, dtype=torch.int64, device=dev)
-        self.send_counts = [int(t.numel()) for t in info.send_rows]
+        world, rank = info.world, info.rank
+        # ---- boundary rows in exchange order
+        peers = [q for q in range(world) if q != rank]
+        order = torch.cat([info.own_rows.to(torch.int64)] + [info.send_rows[q].to(torch.int64) for q in peers]) \
+            if info.bnd_edges.numel() else torch.empty(0, dtype=torch.int64, device=dev)
+        lens = (info.bnd_ptr[1:] - info.bnd_ptr[:-1]).to(torch.int64)
+        new_len = lens[order]
+        self.bnd_ptr = torch.zeros(order.numel() + 1, dtype=torch.int32, device=dev)
+        if order.numel():
+            self.bnd_ptr[1:] = torch.cumsum(new_len, 0).to(torch.int32)
+            starts = info.bnd_ptr[:-1].to(torch.int64)[order]
+            rep = torch.repeat_interleave(torch.arange(order.numel(), device=dev), new_len)
+            within = torch.arange(int(new_len.sum()), device=dev) - self.bnd_ptr[:-1].to(torch.int64)[rep]
+            self.bnd_ind = info.bnd_ind[(starts[rep] + within)].contiguous()
+        else:
+            self.bnd_ind = info.bnd_ind
+        self.bnd_edges = info.bnd_edges[order] if order.numel() else info.bnd_edges
+        self.n_own = int(info.own_rows.numel())
+        # send block of peer q = rows [send_off[q], send_off[q] + send_counts[q]) of P (rank's own block is empty)
+        self.send_counts = [0 if q == rank else int(info.send_rows[q].numel()) for q in range(world)]
         self.recv_counts = [int(t.numel()) for t in info.recv_own_pos]
+        nrecv = sum(self.recv_counts)
+        self.recv_map = torch.cat(info.recv_own_pos).to(torch.int32) if nrecv else torch.empty(0, dtype=torch.int32, device=dev)
+        self.recv_map64 = self.recv_map.to(torch.int64)
+        self.recv_ptr = torch.arange(nrecv + 1, dtype=torch.int32, device=dev)
         self.side = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
         self.bytes_exchanged = 0
+        self._bufs = {}          # F -> (recv, ret): exchange buffers, allocated once
+        self._scales = {}        # cached per-hyperedge scale gathers (identity of s1 / s2 + version)
 
-    def _all_to_all(self, send, send_counts, recv_counts, F):
+    def _buffers(self, F, like):
+        b = self._bufs.get(F)
+        if b is None:
+            nrecv = sum(self.recv_counts)
+            b = (torch.empty((nrecv, F), dtype=like.dtype, device=like.device),
+                 torch.empty((nrecv, F), dtype=like.dtype, device=like.device))
+            self._bufs[F] = b
+        return b
+
+    def _a2a(self, out, inp, out_counts, in_counts, F):
         import torch.distributed as dist
-        recv = torch.empty((sum(recv_counts), F), dtype=send.dtype, device=send.device)
         if self.info.world > 1:
-            dist.all_to_all_single(recv, send.contiguous(), output_split_sizes=recv_counts,
-                                   input_split_sizes=send_counts, group=self.group)
-        self.bytes_exchanged += 4 * F * (sum(send_counts) + sum(recv_counts))
-        return recv
+            dist.all_to_all_single(out, inp, output_split_sizes=out_counts, input_split_sizes=in_counts, group=self.group)
+        self.bytes_exchanged += 4 * F * (sum(out_counts) + sum(in_counts))
+
+    def _edge_scales(self, s1, s2):
+        """scale of the interior and of the boundary hyperedges; gathered once per (s1, s2) contents"""
+        key = tuple((t.data_ptr(), t._version) if t is not None else None for t in (s1, s2))
+        hit = self._scales.get("key")
+        if hit == key:
+            return self._scales["int1"], self._scales["int2"], self._scales["bnd"]
+        info = self.info
+        pick = lambda s, e: None if s is None else s[e].contiguous()
+        i1, i2 = pick(s1, info.int_edges), pick(s2, info.int_edges)
+        bnd = None
+        if s1 is not None or s2 is not None:
+            bnd = (pick(s1, self.bnd_edges) if s1 is not None else 1.0) * (pick(s2, self.bnd_edges) if s2 is not None else 1.0)
+            bnd = bnd.contiguous()
+        self._scales = {"key": key, "int1": i1, "int2": i2, "bnd": bnd}
+        return i1, i2, bnd
 
     def forward(self, X, s1=None, s2=None, a_out=None, a_in=None):
         info, be = self.info, self.backend
@@ -198,7 +248,7 @@ class PartitionedAggregator:
         F = X.shape[1]
         flat = lambda t: None if t is None else t.reshape(-1).contiguous()
         s1, s2, a_out, a_in = flat(s1), flat(s2), flat(a_out), flat(a_in)
-        pick = lambda s, e: None if s is None else s[e].contiguous()
+        si1, si2, sbnd = self._edge_scales(s1, s2)
         Y = torch.empty_like(X)
         use_side = self.side is not None
         if use_side:
@@ -206,28 +256,22 @@ class PartitionedAggregator:
         ctx = torch.cuda.stream(self.side) if use_side else _NullCtx()
         with ctx:
             # boundary stage 1 + exchange (side stream), overlapping the interior kernel below
-            P = be.edge_reduce(info.bnd_ptr, info.bnd_ind, X, a_in)                    # [B_r, F]
-            Q = P                                                                         # completed in place
+            P = be.edge_reduce(self.bnd_ptr, self.bnd_ind, X, a_in)                      # [own | to rank 0 | 1 | ...]
             if info.world > 1:
-                recv = self._all_to_all(P[self.send_cat], self.send_counts, self.recv_counts, F)
-                own = P[info.own_rows].contiguous()                                      # [O_r, F]
-                be.edge_scatter(self.recv_ptr, self.recv_map, recv, None, None, own)     # own[map[i]] += recv[i]
-                back = self._all_to_all(own[self.recv_map.long()], self.recv_counts, self.send_counts, F)
-                Q = P.clone()
-                Q[info.own_rows] = own
-                Q[self.send_cat] = back
-        # interior hyperedges: the single-GPU fused kernel on the local sub-hypergraph
-        be.interior(self.plan, X, pick(s1, info.int_edges), pick(s2, info.int_edges), a_out, a_in, Y)
+                recv, ret = self._buffers(F, P)
+                n_own = self.n_own
+                self._a2a(recv, P[n_own:], self.recv_counts, self.send_counts, F)         # partial rows -> owners
+                own = P[:n_own]
+                be.edge_scatter(self.recv_ptr, self.recv_map, recv, None, None, own)      # own[map[i]] += recv[i]
+                torch.index_select(own, 0, self.recv_map64, out=ret)                      # completed rows each peer asked for
+                self._a2a(P[n_own:], ret, self.send_counts, self.recv_counts, F)          # ... straight back into P
+        # interior hyperedges: the single-GPU kernels on the local sub-hypergraph
+        be.interior(self.plan, X, si1, si2, a_out, a_in, Y)
         if use_side:
             torch.cuda.current_stream().wait_stream(self.side)
-        scale = None
-        if s1 is not None or s2 is not None:
-            scale = (pick(s1, info.bnd_edges) if s1 is not None else 1.0) * (pick(s2, info.bnd_edges) if s2 is not None else 1.0)
-            scale = scale.contiguous()
-        be.edge_scatter(info.bnd_ptr, info.bnd_ind, Q, scale, a_out, Y)                  # boundary stage 2
+        be.edge_scatter(self.bnd_ptr, self.bnd_ind, P, sbnd, a_out, Y)                    # boundary stage 2
         if use_side:
-            for t in (P, Q):
-                t.record_stream(torch.cuda.current_stream())
+            P.record_stream(torch.cuda.current_stream())
         return Y
 
 

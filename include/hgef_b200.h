@@ -108,9 +108,10 @@ HG_API int hg_mtx_fill(const hgMtx *mtx, int64_t *h_rows, int64_t *h_cols);
 HG_API int hg_mtx_close(hgMtx *mtx);
 
 /* ------------------------------------------------------------------------- *
- * Aggregation plan: everything derived once from the balancer output so that the
- * per-call path is a single fused launch.  Borrowed pointers (d_key .. d_t_indices)
- * must outlive the plan.  Validates every index (HG_EGRAPH).
+ * Aggregation plan: everything derived once from the balancer output (segment -> hyperedge map, heavy
+ * hyperedges, the CSR of H, the row programs of the two stages) so that the per-call path is two kernel
+ * launches and no allocation.  Borrowed pointers (d_key .. d_t_indices) must outlive the plan.
+ * Validates every index (HG_EGRAPH).
  *   nseg   = nkey - 1 (segments), ngroup = len(group_row)
  * ------------------------------------------------------------------------- */
 typedef struct hgPlan hgPlan;
@@ -127,12 +128,19 @@ HG_API int hg_plan_info(const hgPlan *plan, int64_t *nseg, int64_t *nheavy_edges
 /* Number of this library's kernels launched through the plan so far (aggregation calls only). */
 HG_API int hg_plan_launches(const hgPlan *plan, int64_t *kernels);
 
-/* Diagnostic: the 8 control words of the last ring-form launch (ticket counter, give-up flag and, with the
- * tuning knob ring_prof = 1, a clock breakdown of the control and worker warps in kilo-clocks). */
+/* Sizes the plan's per-call buffers (hyperedge features [num_edges, F], heavy-hyperedge scratch) for feature
+ * lengths up to F_max, so that no later hg_aggr_forward allocates: call it before capturing the op into a
+ * CUDA graph or using a new, wider F inside one.  A buffer that has to grow is never freed before the plan
+ * is destroyed (a launch in flight or a captured graph may still name it); growing while `stream` is being
+ * captured is refused with HG_EINVAL.  The reference allocates its output inside every call
+ * (torch::zeros, hgnnaggr_cuda.cu:374) and keeps no state. */
+HG_API int hg_plan_reserve(hgPlan *plan, int32_t F_max, void *stream);
+
+/* Diagnostic (lab library only; zeros otherwise): control words of the last experimental-form launch. */
 HG_API int hg_plan_debug(hgPlan *plan, int32_t *h_out8, void *stream);
 
-/* Synchronises `stream` and reports (HG_ECUDA) any fault of the launches issued with this plan,
- * including the fused kernel's bounded-wait give-up.  The reference has no equivalent: it never
+/* Synchronises `stream` and reports (HG_ECUDA) any fault of the launches issued with this plan (and, in the
+ * lab library, an experimental form's bounded-wait give-up).  The reference has no equivalent: it never
  * checks a launch (hgnnaggr_cuda.cu:383-404). */
 HG_API int hg_plan_check(hgPlan *plan, void *stream);
 
@@ -140,24 +148,27 @@ HG_API int hg_plan_check(hgPlan *plan, void *stream);
 enum {
   HG_ACCUMULATE = 1,     /* do not zero-fill Y first (reference: torch::zeros, hgnnaggr_cuda.cu:374) */
   HG_FORCE_SCALAR = 4,   /* disable the 128-bit path (testing) */
-  HG_TWO_PASS = 8,       /* always memset + segment kernels (the form chosen for small / long-segment graphs) */
-  HG_FORCE_FUSED = 16,   /* always the single persistent scatter launch */
-  HG_FORCE_PULL = 32,    /* always the gather-only two-phase form with shared-memory staging (Xe through L2/HBM,
-                            no reductions; the earlier form, kept for A/B) */
-  HG_FORCE_STREAM = 64,  /* always the stream form: both stages as register-only row streams, two launches, the
-                            hyperedge features make a round trip through HBM */
-  HG_FORCE_FSTREAM = 256, /* always the fused stream form: both stages as register-only row streams in ONE persistent
-                            launch, hyperedge features handed over through the L2 and discarded there (the form chosen
-                            when Y exceeds the L2) */
-  HG_FORCE_RING = 128    /* always the ring form: both stages in one persistent launch, rows moved by TMA bulk copies
-                            into a shared-memory ring, hyperedge features handed over through the L2 and discarded
-                            there (the form chosen for rows >= 512 B when Y exceeds the L2) */
+  HG_TWO_PASS = 8,       /* always memset + segment kernels (the form chosen when Y fits the L2) */
+  HG_FORCE_STREAM = 64,  /* always the stream form: both stages as register-only row streams, two launches (the second
+                            a programmatic dependent launch), the hyperedge features make one round trip through the
+                            L2 / HBM (the form chosen when Y exceeds the L2) */
+  /* EXPERIMENTAL forms, built only into libhgef_b200_lab.so (make -C hypergef_b200/csrc lab; HG_EINVAL in the
+   * product library).  All of them merge both stages into one launch; all are measured slower than the stream
+   * form and are kept as evidence: */
+  HG_FORCE_FUSED = 16,   /* single persistent scatter launch (red.v4 into Y; round 1) */
+  HG_FORCE_PULL = 32,    /* gather-only two-phase form with shared-memory staging (round 1) */
+  HG_FORCE_RING = 128,   /* one persistent launch, rows moved by TMA bulk copies (cp.async.bulk) into a shared-memory
+                            ring, hyperedge features handed over through the L2 and discarded there */
+  HG_FORCE_FSTREAM = 256 /* one persistent launch of register-only row streams with the same hand-over */
 };
 
 /* ------------------------------------------------------------------------- *
  * Fused two-stage aggregation
  *     Y = diag(a_out) . H . diag(s1*s2) . H^T . diag(a_in) . X
- * in one pass over the balancer segments; the hyperedge feature never goes to DRAM.
+ * as one C-ABI call.  Small graphs (Y fits the L2): one warp per balancer segment, the hyperedge feature stays in
+ * registers, vector reductions into a zero-filled Y.  Large graphs: stage A (balancer segments -> hyperedge
+ * features Xe) and stage B (Xe -> Y, every row written once, no atomics) as two back-to-back launches; Xe is a
+ * plan-owned [num_edges, F] buffer that passes through the L2 / HBM between them.
  * Replaces hgnnaggr_fp_cuda (source/hgnnaggr/hgnnaggr_cuda.cu:350-406) with
  * s1=degE, s2=W, a_out=degV; unignnaggrdeg_fp_cuda (source/unignnaggr/unignnaggr_cuda.cu:392-447)
  * with s2=NULL; unignnaggr_fp_cuda (:449-488) with all scales NULL.  Any scale may

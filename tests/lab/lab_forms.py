@@ -1,0 +1,139 @@
+"""Parity of the EXPERIMENTAL single-launch kernel forms (libhgef_b200_lab.so) with the oracle.
+
+Not collected by the normal run: tests/test_lab.py executes this file in a subprocess with
+HGEF_B200_LIB pointing at the lab library (the product library refuses these forms with HG_EINVAL).
+The forms: ring (TMA bulk row copies into a shared-memory ring), fstream (register row streams), both with the
+hyperedge features handed over through the L2 inside ONE persistent launch and discarded there; fused / pull
+(round 1).  All parity-green, all slower than the shipped stream form.
+"""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+import hypergef_b200 as hgef
+from hypergef_b200 import HyperGraph, ops, synth, _native
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+LAB_FORMS = {"fused": _native.HG_FORCE_FUSED, "pull": _native.HG_FORCE_PULL, "ring": _native.HG_FORCE_RING,
+             "fstream": _native.HG_FORCE_FSTREAM}
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def cuda_device():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    assert "lab" in _native.LIB_PATH, "run through tests/test_lab.py (HGEF_B200_LIB = the lab library)"
+    return torch.device("cuda:0")
+
+
+@pytest.mark.parametrize("form", sorted(LAB_FORMS))
+@pytest.mark.parametrize("shape,F", [("cora", 32), ("pubmed", 64), ("dblp", 128), ("walmart", 32), ("pubmed", 200), ("dblp", 512)])
+def test_lab_forms_on_baseline_shapes(form, shape, F, cuda_device):
+    data = synth.make_shape(shape, seed=0)
+    hg = HyperGraph(data, cuda_device, data.dataset)
+    plan = ops.get_plan(hg.group_key, hg.group_row, hg.group_start, hg.group_end, hg.H_T_colind, hg.num_nodes, hg.num_edges)
+    X = torch.randn(hg.num_nodes, F, generator=torch.Generator().manual_seed(1))
+    W = torch.rand(hg.num_edges, generator=torch.Generator().manual_seed(2)) + 0.5
+    want = orc.c_aggr_formula(_np(hg.H_T_csrptr), _np(hg.H_T_colind), X, s1=_np(hg.degE).ravel() * W.numpy(), a_out=_np(hg.degV))
+    out = torch.full((hg.num_nodes, F), float("nan"), device=cuda_device)
+    ops.aggregate(plan, X.to(cuda_device), s1=hg.degE, s2=W.to(cuda_device), a_out=hg.degV, out=out, flags=LAB_FORMS[form])
+    plan.check()
+    assert orc.rel_err(_np(out), want) < TOL
+
+
+RING_KNOBS = ("ring_workers", "ring_ctas", "ring_qd", "ring_chunk", "ring_kb", "ring_item_kb", "ring_lag_b", "ring_lag_c",
+              "ring_discard", "ring_pol_x", "ring_pol_xe_w", "ring_pol_xe_r", "ring_pol_y")
+
+
+@pytest.mark.parametrize("shape,replicas", [("pubmed", 3), ("walmart", 1), ("dblp", 2)])
+def test_ring_form_configurations(shape, replicas, cuda_device):
+    """The ring form (one persistent launch: TMA row ring, A / B / discard items in one ticket order) under
+    every geometry knob -- consumers, ring size, chunk length, item size, lags down to 0 (dependencies
+    really wait), discard on / off, eviction hints -- forward and transposed, EVERY feature length against
+    the fp64 C oracle.  Results are bit-identical run to run where the graph has no heavy hyperedge."""
+    data = synth.make_shape(shape, replicas=replicas, seed=3)
+    hg = HyperGraph(data, cuda_device, data.dataset)
+    N, M = hg.num_nodes, hg.num_edges
+    plan = ops.get_plan(hg.group_key, hg.group_row, hg.group_start, hg.group_end, hg.H_T_colind, N, M)
+    W = torch.rand(M, device=cuda_device) + 0.5
+    ptr, ind = _np(hg.H_T_csrptr), _np(hg.H_T_colind)
+    combos = [dict(), dict(ring_lag_b=0, ring_lag_c=0), dict(ring_workers=3, ring_ctas=1, ring_kb=160),
+              dict(ring_workers=16, ring_qd=2, ring_chunk=2, ring_item_kb=8),
+              dict(ring_chunk=32, ring_item_kb=256, ring_kb=64), dict(ring_discard=0, ring_lag_b=1000000),
+              dict(ring_kb=16, ring_item_kb=4, ring_lag_b=3, ring_lag_c=1),
+              dict(ring_pol_x=0, ring_pol_xe_w=0, ring_pol_xe_r=1, ring_pol_y=0, ring_ctas=3, ring_kb=48),
+              dict(ring_workers=1, ring_qd=2, ring_chunk=5, ring_ctas=4, ring_kb=32)]
+    try:
+        for F in (4, 20, 32, 64, 100, 128, 256, 384, 512, 640, 1056):
+            X = torch.randn(N, F, device=cuda_device)
+            s_edge = _np(hg.degE).ravel() * _np(W)
+            want = orc.c_aggr_formula(ptr, ind, X.cpu(), s1=s_edge, a_out=_np(hg.degV))
+            want_t = orc.c_aggr_formula(ptr, ind, X.cpu(), s1=s_edge, a_in=_np(hg.degV))
+            for knobs in combos:
+                ops.tune(**{k: None for k in RING_KNOBS})
+                ops.tune(**knobs)
+                out = torch.full((N, F), float("nan"), device=cuda_device)
+                ops.aggregate(plan, X, s1=hg.degE, s2=W, a_out=hg.degV, out=out, flags=_native.HG_FORCE_RING)
+                plan.check()
+                assert orc.rel_err(_np(out), want) < TOL, (shape, F, knobs)
+                out_t = ops.aggregate(plan, X, s1=hg.degE, s2=W, a_in=hg.degV, flags=_native.HG_FORCE_RING)
+                assert orc.rel_err(_np(out_t), want_t) < TOL, (shape, F, knobs, "transposed")
+                if plan.nheavy_edges == 0:
+                    again = ops.aggregate(plan, X, s1=hg.degE, s2=W, a_out=hg.degV, flags=_native.HG_FORCE_RING)
+                    assert torch.equal(again, out), (shape, F, knobs, "run-to-run")
+                plan.check()
+    finally:
+        ops.tune(**{k: None for k in RING_KNOBS})
+
+
+FS_KNOBS = ("fs_batch", "fs_sw", "fs_occ", "fs_pipe", "fs_ctas", "fs_item_kb", "fs_lag_b", "fs_lag_c", "fs_discard", "fs_pol_x", "fs_pol_xe_w",
+            "fs_pol_y")
+
+
+@pytest.mark.parametrize("shape,replicas", [("pubmed", 3), ("walmart", 1), ("dblp", 2)])
+def test_fused_stream_form_configurations(shape, replicas, cuda_device):
+    """The fused stream form (one persistent launch: register row streams, A / B / discard items in one
+    ticket order) under every knob -- sub-warp width, occupancy, pipelining, item size, lags down to 0
+    (dependencies really wait), discard on / off, eviction hints -- forward and transposed, EVERY feature
+    length against the fp64 C oracle; bit-identical run to run where the graph has no heavy hyperedge."""
+    data = synth.make_shape(shape, replicas=replicas, seed=3)
+    hg = HyperGraph(data, cuda_device, data.dataset)
+    N, M = hg.num_nodes, hg.num_edges
+    plan = ops.get_plan(hg.group_key, hg.group_row, hg.group_start, hg.group_end, hg.H_T_colind, N, M)
+    W = torch.rand(M, device=cuda_device) + 0.5
+    ptr, ind = _np(hg.H_T_csrptr), _np(hg.H_T_colind)
+    combos = [dict(), dict(fs_lag_b=0, fs_lag_c=0, fs_batch=1), dict(fs_occ=2, fs_item_kb=4), dict(fs_occ=1, fs_pipe=0, fs_batch=1),
+              dict(fs_sw=16, fs_item_kb=1, fs_lag_b=5, fs_lag_c=2, fs_batch=8), dict(fs_sw=8, fs_ctas=1, fs_item_kb=64),
+              dict(fs_discard=0, fs_lag_b=1000000), dict(fs_pol_x=0, fs_pol_xe_w=0, fs_pol_y=0, fs_pipe=1),
+              dict(fs_item_kb=256, fs_ctas=2, fs_batch=2)]
+    try:
+        for F in (4, 20, 32, 64, 100, 128, 256, 384, 512, 640, 1056):
+            X = torch.randn(N, F, device=cuda_device)
+            s_edge = _np(hg.degE).ravel() * _np(W)
+            want = orc.c_aggr_formula(ptr, ind, X.cpu(), s1=s_edge, a_out=_np(hg.degV))
+            want_t = orc.c_aggr_formula(ptr, ind, X.cpu(), s1=s_edge, a_in=_np(hg.degV))
+            for knobs in combos:
+                ops.tune(**{k: None for k in FS_KNOBS})
+                ops.tune(**knobs)
+                out = torch.full((N, F), float("nan"), device=cuda_device)
+                ops.aggregate(plan, X, s1=hg.degE, s2=W, a_out=hg.degV, out=out, flags=_native.HG_FORCE_FSTREAM)
+                plan.check()
+                assert orc.rel_err(_np(out), want) < TOL, (shape, F, knobs)
+                out_t = ops.aggregate(plan, X, s1=hg.degE, s2=W, a_in=hg.degV, flags=_native.HG_FORCE_FSTREAM)
+                assert orc.rel_err(_np(out_t), want_t) < TOL, (shape, F, knobs, "transposed")
+                if plan.nheavy_edges == 0:
+                    again = ops.aggregate(plan, X, s1=hg.degE, s2=W, a_out=hg.degV, flags=_native.HG_FORCE_FSTREAM)
+                    assert torch.equal(again, out), (shape, F, knobs, "run-to-run")
+                plan.check()
+    finally:
+        ops.tune(**{k: None for k in FS_KNOBS})
+
+

@@ -19,20 +19,13 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-5
 
 
-@pytest.fixture(params=["auto", "fused", "two_pass", "pull", "stream", "stream2", "ring", "fstream"])
+@pytest.fixture(params=["auto", "two_pass", "stream"])
 def kernel_form(request):
-    """Run a test with the library's own choice of kernel form, then with each form forced
-    (the large-graph forms are only chosen on their own when Y exceeds the L2).  "stream" is the
-    single persistent launch, "stream2" the same row streams as two launches."""
-    import os
-    ops.DEFAULT_FLAGS = {"auto": 0, "fused": _native.HG_FORCE_FUSED, "two_pass": _native.HG_TWO_PASS,
-                         "pull": _native.HG_FORCE_PULL, "stream": _native.HG_FORCE_STREAM,
-                         "stream2": _native.HG_FORCE_STREAM, "ring": _native.HG_FORCE_RING,
-                         "fstream": _native.HG_FORCE_FSTREAM}[request.param]
-    if request.param in ("stream", "stream2"):
-        os.environ["HGEF_ST_FUSED"] = "1" if request.param == "stream" else "0"
+    """Run a test with the library's own choice of kernel form, then with each product form forced (the
+    stream form is only chosen on its own when Y exceeds the L2).  The experimental single-launch forms live
+    in the lab library and are tested by tests/lab/ (tests/test_lab.py)."""
+    ops.DEFAULT_FLAGS = {"auto": 0, "two_pass": _native.HG_TWO_PASS, "stream": _native.HG_FORCE_STREAM}[request.param]
     yield request.param
-    os.environ.pop("HGEF_ST_FUSED", None)
     ops.DEFAULT_FLAGS = 0
 
 
@@ -281,146 +274,115 @@ def test_full_size_properties(cuda_device, kernel_form):
     assert ((yu.double().sum(0) - want).abs().max() / want.abs().max()).item() < 1e-6
 
 
+ST_KNOBS = ("st_slab", "st_sw", "st_l", "st_ctas", "st_occ", "st_pipe", "st_cs", "st_pdl", "stream_min_mb")
+
+
 @pytest.mark.parametrize("shape,replicas", [("pubmed", 3), ("walmart", 1), ("dblp", 2)])
-def test_stream_form_configurations(shape, replicas, cuda_device, monkeypatch):
-    """The stream form under every scheduling knob (item length, column slabs, lag, one launch or two),
-    forward and transposed, against the two-pass kernels and (one configuration) the fp64 oracle.
-    Each fused configuration is bit-identical run to run (fixed summation order, no atomics for light
-    hyperedges) -- checked where the graph has no heavy hyperedge."""
+def test_stream_form_configurations(shape, replicas, cuda_device):
+    """The stream form (the shipped large-graph form: stage A and stage B as two launches, B a programmatic
+    dependent launch of A, self-resetting ticket counters) under every geometry knob -- item length, column
+    slabs, sub-warp width, occupancy, pipelining, store hint, PDL on / off -- forward and transposed, EVERY
+    feature length against the fp64 C oracle, element-wise against the sum of the magnitudes of the terms as
+    well as against the largest value.  Bit-identical run to run (fixed summation order, no atomics for light
+    hyperedges) where the graph has no heavy hyperedge."""
     data = synth.make_shape(shape, replicas=replicas, seed=3)
     hg = HyperGraph(data, cuda_device, data.dataset)
     N, M = hg.num_nodes, hg.num_edges
     plan = ops.get_plan(hg.group_key, hg.group_row, hg.group_start, hg.group_end, hg.H_T_colind, N, M)
     W = torch.rand(M, device=cuda_device) + 0.5
-    for F in (4, 20, 32, 64, 100, 128, 256, 384, 512, 640):
-        X = torch.randn(N, F, device=cuda_device)
-        ref = ops.aggregate(plan, X, s1=hg.degE, s2=W, a_out=hg.degV, flags=_native.HG_TWO_PASS)
-        ref_t = ops.aggregate(plan, X, s1=hg.degE, s2=W, a_in=hg.degV, flags=_native.HG_TWO_PASS)
-        scale, scale_t = ref.abs().max().item(), ref_t.abs().max().item()
-        combos = [dict(HGEF_ST_FUSED="1"), dict(HGEF_ST_FUSED="0"), dict(HGEF_ST_FUSED="1", HGEF_ST_L="16", HGEF_ST_LAG="0"),
-                  dict(HGEF_ST_FUSED="1", HGEF_ST_L="16", HGEF_ST_LAG="1000000"),
-                  dict(HGEF_ST_FUSED="1", HGEF_ST_L="48", HGEF_ST_SLAB="32"),
-                  dict(HGEF_ST_FUSED="1", HGEF_ST_L="256", HGEF_ST_SLAB="128", HGEF_ST_CTAS="1"),
-                  dict(HGEF_ST_OCC="4"), dict(HGEF_ST_PIPE="0", HGEF_ST_L="32"), dict(HGEF_ST_PIPE="1", HGEF_ST_FUSED="1"),
-                  dict(HGEF_ST_SW="16"), dict(HGEF_ST_SW="8", HGEF_ST_OCC="4"), dict(HGEF_ST_SW="4", HGEF_ST_FUSED="1"),
-                  dict(HGEF_ST_FUSED="0", HGEF_ST_SLAB="64", HGEF_ST_L="16")]
-        for env in combos:
-            for k in ("HGEF_ST_FUSED", "HGEF_ST_L", "HGEF_ST_LAG", "HGEF_ST_SLAB", "HGEF_ST_CTAS", "HGEF_ST_OCC", "HGEF_ST_SW", "HGEF_ST_PIPE"):
-                monkeypatch.delenv(k, raising=False)
-            for k, v in env.items():
-                monkeypatch.setenv(k, v)
+    ptr, ind = _np(hg.H_T_csrptr), _np(hg.H_T_colind)
+    s_edge = _np(hg.degE).ravel() * _np(W)
+    combos = [dict(), dict(st_pdl=0), dict(st_l=16), dict(st_l=48, st_slab=32), dict(st_l=256, st_slab=128, st_ctas=1),
+              dict(st_occ=4), dict(st_pipe=0, st_l=32), dict(st_pipe=1), dict(st_sw=16), dict(st_sw=8, st_occ=4),
+              dict(st_sw=4, st_cs=0), dict(st_slab=64, st_l=16, st_pdl=0)]
+    try:
+        for F in (4, 20, 32, 64, 100, 128, 256, 384, 512, 640):
+            X = torch.randn(N, F, device=cuda_device)
+            want = orc.c_aggr_formula(ptr, ind, X.cpu(), s1=s_edge, a_out=_np(hg.degV))
+            bound = orc.c_aggr_formula(ptr, ind, X.cpu().abs(), s1=np.abs(s_edge), a_out=np.abs(_np(hg.degV)))
+            want_t = orc.c_aggr_formula(ptr, ind, X.cpu(), s1=s_edge, a_in=_np(hg.degV))
+            for knobs in combos:
+                ops.tune(**{k: None for k in ST_KNOBS})
+                ops.tune(**knobs)
+                out = torch.full((N, F), float("nan"), device=cuda_device)
+                ops.aggregate(plan, X, s1=hg.degE, s2=W, a_out=hg.degV, out=out, flags=_native.HG_FORCE_STREAM)
+                assert orc.rel_err(_np(out), want) < TOL, (shape, F, knobs)
+                assert orc.rel_err_terms(_np(out), want, bound) < TOL, (shape, F, knobs, "element-wise")
+                out_t = ops.aggregate(plan, X, s1=hg.degE, s2=W, a_in=hg.degV, flags=_native.HG_FORCE_STREAM)
+                assert orc.rel_err(_np(out_t), want_t) < TOL, (shape, F, knobs, "transposed")
+                if plan.nheavy_edges == 0:
+                    again = ops.aggregate(plan, X, s1=hg.degE, s2=W, a_out=hg.degV, flags=_native.HG_FORCE_STREAM)
+                    assert torch.equal(again, out), (shape, F, knobs, "run-to-run")
+                plan.check()
+    finally:
+        ops.tune(**{k: None for k in ST_KNOBS})
+
+
+def test_odd_feature_lengths_on_a_large_graph_use_padded_rows(cuda_device):
+    """F % 4 != 0 on a graph whose Y exceeds the L2 (threshold lowered through the tuning table so that a
+    small graph takes that route): the stream kernels run on rows padded to the next multiple of 4 instead of
+    the scalar-atomic path; the result equals the oracle and NaNs in the output buffer do not leak."""
+    data = synth.make_shape("dblp", replicas=2, seed=4)
+    hg = HyperGraph(data, cuda_device, data.dataset)
+    N, M = hg.num_nodes, hg.num_edges
+    plan = ops.get_plan(hg.group_key, hg.group_row, hg.group_start, hg.group_end, hg.H_T_colind, N, M)
+    ptr, ind = _np(hg.H_T_csrptr), _np(hg.H_T_colind)
+    try:
+        ops.tune(stream_min_mb=0)
+        for F in (1, 3, 7, 30, 101):
+            X = torch.randn(N, F, device=cuda_device)
+            want = orc.c_aggr_formula(ptr, ind, X.cpu(), s1=_np(hg.degE), a_out=_np(hg.degV))
+            k0 = plan.kernels_launched()
             out = torch.full((N, F), float("nan"), device=cuda_device)
-            ops.aggregate(plan, X, s1=hg.degE, s2=W, a_out=hg.degV, out=out, flags=_native.HG_FORCE_STREAM)
-            assert ((out - ref).abs().max().item() / scale) < TOL, (shape, F, env)
-            out_t = ops.aggregate(plan, X, s1=hg.degE, s2=W, a_in=hg.degV, flags=_native.HG_FORCE_STREAM)
-            assert ((out_t - ref_t).abs().max().item() / scale_t) < TOL, (shape, F, env, "transposed")
-            if plan.nheavy_edges == 0:
-                again = ops.aggregate(plan, X, s1=hg.degE, s2=W, a_out=hg.degV, flags=_native.HG_FORCE_STREAM)
-                assert torch.equal(again, out), (shape, F, env, "run-to-run")
+            ops.aggregate(plan, X, s1=hg.degE, a_out=hg.degV, out=out)
             plan.check()
-        if F == 64:
-            want = orc.c_aggr_formula(_np(hg.H_T_csrptr), _np(hg.H_T_colind), X.cpu(), s1=_np(hg.degE).ravel() * _np(W),
-                                      a_out=_np(hg.degV))
-            assert orc.rel_err(_np(out), want) < TOL
+            assert plan.kernels_launched() - k0 == 4 + (1 if plan.nheavy_segs else 0)   # pad, A, B, unpad
+            assert orc.rel_err(_np(out), want) < TOL, F
+    finally:
+        ops.tune(stream_min_mb=None)
 
 
-RING_KNOBS = ("ring_workers", "ring_ctas", "ring_qd", "ring_chunk", "ring_kb", "ring_item_kb", "ring_lag_b", "ring_lag_c",
-              "ring_discard", "ring_pol_x", "ring_pol_xe_w", "ring_pol_xe_r", "ring_pol_y")
-
-
-@pytest.mark.parametrize("shape,replicas", [("pubmed", 3), ("walmart", 1), ("dblp", 2)])
-def test_ring_form_configurations(shape, replicas, cuda_device):
-    """The ring form (one persistent launch: TMA row ring, A / B / discard items in one ticket order) under
-    every geometry knob -- consumers, ring size, chunk length, item size, lags down to 0 (dependencies
-    really wait), discard on / off, eviction hints -- forward and transposed, EVERY feature length against
-    the fp64 C oracle.  Results are bit-identical run to run where the graph has no heavy hyperedge."""
-    data = synth.make_shape(shape, replicas=replicas, seed=3)
+def test_plan_reserve_and_capture_never_allocate(cuda_device):
+    """hg_plan_reserve sizes the per-call buffers once; a call that would have to grow one while the stream is
+    being captured is refused (ValueError) instead of allocating inside the capture; a buffer that grows is not
+    freed under a graph that still uses it (the earlier graph replays correctly afterwards)."""
+    data = synth.make_shape("pubmed", replicas=2, seed=6)
     hg = HyperGraph(data, cuda_device, data.dataset)
     N, M = hg.num_nodes, hg.num_edges
     plan = ops.get_plan(hg.group_key, hg.group_row, hg.group_start, hg.group_end, hg.H_T_colind, N, M)
-    W = torch.rand(M, device=cuda_device) + 0.5
-    ptr, ind = _np(hg.H_T_csrptr), _np(hg.H_T_colind)
-    combos = [dict(), dict(ring_lag_b=0, ring_lag_c=0), dict(ring_workers=3, ring_ctas=1, ring_kb=160),
-              dict(ring_workers=16, ring_qd=2, ring_chunk=2, ring_item_kb=8),
-              dict(ring_chunk=32, ring_item_kb=256, ring_kb=64), dict(ring_discard=0, ring_lag_b=1000000),
-              dict(ring_kb=16, ring_item_kb=4, ring_lag_b=3, ring_lag_c=1),
-              dict(ring_pol_x=0, ring_pol_xe_w=0, ring_pol_xe_r=1, ring_pol_y=0, ring_ctas=3, ring_kb=48),
-              dict(ring_workers=1, ring_qd=2, ring_chunk=5, ring_ctas=4, ring_kb=32)]
-    try:
-        for F in (4, 20, 32, 64, 100, 128, 256, 384, 512, 640, 1056):
-            X = torch.randn(N, F, device=cuda_device)
-            s_edge = _np(hg.degE).ravel() * _np(W)
-            want = orc.c_aggr_formula(ptr, ind, X.cpu(), s1=s_edge, a_out=_np(hg.degV))
-            want_t = orc.c_aggr_formula(ptr, ind, X.cpu(), s1=s_edge, a_in=_np(hg.degV))
-            for knobs in combos:
-                ops.tune(**{k: None for k in RING_KNOBS})
-                ops.tune(**knobs)
-                out = torch.full((N, F), float("nan"), device=cuda_device)
-                ops.aggregate(plan, X, s1=hg.degE, s2=W, a_out=hg.degV, out=out, flags=_native.HG_FORCE_RING)
-                plan.check()
-                assert orc.rel_err(_np(out), want) < TOL, (shape, F, knobs)
-                out_t = ops.aggregate(plan, X, s1=hg.degE, s2=W, a_in=hg.degV, flags=_native.HG_FORCE_RING)
-                assert orc.rel_err(_np(out_t), want_t) < TOL, (shape, F, knobs, "transposed")
-                if plan.nheavy_edges == 0:
-                    again = ops.aggregate(plan, X, s1=hg.degE, s2=W, a_out=hg.degV, flags=_native.HG_FORCE_RING)
-                    assert torch.equal(again, out), (shape, F, knobs, "run-to-run")
-                plan.check()
-    finally:
-        ops.tune(**{k: None for k in RING_KNOBS})
+    flags = _native.HG_FORCE_STREAM
+    X32 = torch.randn(N, 32, device=cuda_device)
+    Y32 = torch.empty_like(X32)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        plan.reserve(32)
+        g32 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g32, stream=side):      # first use of the plan, captured: reserve made it legal
+            ops.aggregate(plan, X32, s1=hg.degE, a_out=hg.degV, out=Y32, flags=flags)
+        X64 = torch.randn(N, 64, device=cuda_device)
+        Y64 = torch.empty_like(X64)
+        g64 = torch.cuda.CUDAGraph()
+        with pytest.raises(ValueError):
+            with torch.cuda.graph(g64, stream=side):  # wider F without a reserve: must refuse, not allocate
+                ops.aggregate(plan, X64, s1=hg.degE, a_out=hg.degV, out=Y64, flags=flags)
+    torch.cuda.synchronize()
+    plan.reserve(64)                                  # grows the buffer g32 was captured with: it must stay alive
+    want64 = ops.aggregate(plan, X64, s1=hg.degE, a_out=hg.degV, flags=_native.HG_TWO_PASS)
+    got64 = ops.aggregate(plan, X64, s1=hg.degE, a_out=hg.degV, flags=flags)
+    assert ((got64 - want64).abs().max() / want64.abs().max()).item() < TOL
+    Y32.fill_(float("nan"))
+    g32.replay()
+    torch.cuda.synchronize()
+    want32 = ops.aggregate(plan, X32, s1=hg.degE, a_out=hg.degV, flags=_native.HG_TWO_PASS)
+    assert ((Y32 - want32).abs().max() / want32.abs().max()).item() < TOL
+    plan.check()
 
 
-FS_KNOBS = ("fs_batch", "fs_sw", "fs_occ", "fs_pipe", "fs_ctas", "fs_item_kb", "fs_lag_b", "fs_lag_c", "fs_discard", "fs_pol_x", "fs_pol_xe_w",
-            "fs_pol_y")
-
-
-@pytest.mark.parametrize("shape,replicas", [("pubmed", 3), ("walmart", 1), ("dblp", 2)])
-def test_fused_stream_form_configurations(shape, replicas, cuda_device):
-    """The fused stream form (one persistent launch: register row streams, A / B / discard items in one
-    ticket order) under every knob -- sub-warp width, occupancy, pipelining, item size, lags down to 0
-    (dependencies really wait), discard on / off, eviction hints -- forward and transposed, EVERY feature
-    length against the fp64 C oracle; bit-identical run to run where the graph has no heavy hyperedge."""
-    data = synth.make_shape(shape, replicas=replicas, seed=3)
-    hg = HyperGraph(data, cuda_device, data.dataset)
-    N, M = hg.num_nodes, hg.num_edges
-    plan = ops.get_plan(hg.group_key, hg.group_row, hg.group_start, hg.group_end, hg.H_T_colind, N, M)
-    W = torch.rand(M, device=cuda_device) + 0.5
-    ptr, ind = _np(hg.H_T_csrptr), _np(hg.H_T_colind)
-    combos = [dict(), dict(fs_lag_b=0, fs_lag_c=0, fs_batch=1), dict(fs_occ=2, fs_item_kb=4), dict(fs_occ=1, fs_pipe=0, fs_batch=1),
-              dict(fs_sw=16, fs_item_kb=1, fs_lag_b=5, fs_lag_c=2, fs_batch=8), dict(fs_sw=8, fs_ctas=1, fs_item_kb=64),
-              dict(fs_discard=0, fs_lag_b=1000000), dict(fs_pol_x=0, fs_pol_xe_w=0, fs_pol_y=0, fs_pipe=1),
-              dict(fs_item_kb=256, fs_ctas=2, fs_batch=2)]
-    try:
-        for F in (4, 20, 32, 64, 100, 128, 256, 384, 512, 640, 1056):
-            X = torch.randn(N, F, device=cuda_device)
-            s_edge = _np(hg.degE).ravel() * _np(W)
-            want = orc.c_aggr_formula(ptr, ind, X.cpu(), s1=s_edge, a_out=_np(hg.degV))
-            want_t = orc.c_aggr_formula(ptr, ind, X.cpu(), s1=s_edge, a_in=_np(hg.degV))
-            for knobs in combos:
-                ops.tune(**{k: None for k in FS_KNOBS})
-                ops.tune(**knobs)
-                out = torch.full((N, F), float("nan"), device=cuda_device)
-                ops.aggregate(plan, X, s1=hg.degE, s2=W, a_out=hg.degV, out=out, flags=_native.HG_FORCE_FSTREAM)
-                plan.check()
-                assert orc.rel_err(_np(out), want) < TOL, (shape, F, knobs)
-                out_t = ops.aggregate(plan, X, s1=hg.degE, s2=W, a_in=hg.degV, flags=_native.HG_FORCE_FSTREAM)
-                assert orc.rel_err(_np(out_t), want_t) < TOL, (shape, F, knobs, "transposed")
-                if plan.nheavy_edges == 0:
-                    again = ops.aggregate(plan, X, s1=hg.degE, s2=W, a_out=hg.degV, flags=_native.HG_FORCE_FSTREAM)
-                    assert torch.equal(again, out), (shape, F, knobs, "run-to-run")
-                plan.check()
-    finally:
-        ops.tune(**{k: None for k in FS_KNOBS})
-
-
-@pytest.mark.parametrize("form", ["two_pass", "stream", "stream_fused", "fused", "pull", "ring", "fstream"])
-def test_cuda_graph_capture_and_replay(form, cuda_device, monkeypatch):
+@pytest.mark.parametrize("form", ["two_pass", "stream"])
+def test_cuda_graph_capture_and_replay(form, cuda_device):
     """Every kernel form is capture-safe after one eager warm-up call (the first call of a plan may allocate its
     scratch): a captured aggregation replays correctly on new contents of the same input buffer."""
-    flags = {"two_pass": _native.HG_TWO_PASS, "stream": _native.HG_FORCE_STREAM, "stream_fused": _native.HG_FORCE_STREAM,
-             "fused": _native.HG_FORCE_FUSED, "pull": _native.HG_FORCE_PULL, "ring": _native.HG_FORCE_RING,
-             "fstream": _native.HG_FORCE_FSTREAM}[form]
-    if form == "stream_fused":
-        monkeypatch.setenv("HGEF_ST_FUSED", "1")
+    flags = {"two_pass": _native.HG_TWO_PASS, "stream": _native.HG_FORCE_STREAM}[form]
     data = synth.make_shape("pubmed", replicas=2, seed=5)
     hg = HyperGraph(data, cuda_device, data.dataset)
     plan = ops.get_plan(hg.group_key, hg.group_row, hg.group_start, hg.group_end, hg.H_T_colind, hg.num_nodes,
@@ -599,8 +561,7 @@ def test_ragged_and_degenerate_graphs(cuda_device):
             want = orc.c_aggr_formula(ptr, ind, X, s1=_np(hg.degE), a_out=_np(hg.degV))
             out = torch.full((N, F), float("nan"), device=cuda_device)
             plan = ops.get_plan(hg.group_key, hg.group_row, hg.group_start, hg.group_end, hg.H_T_colind, N, hg.num_edges)
-            for flags in (0, _native.HG_TWO_PASS, _native.HG_FORCE_FUSED, _native.HG_FORCE_PULL, _native.HG_FORCE_STREAM,
-                          _native.HG_FORCE_RING, _native.HG_FORCE_FSTREAM):
+            for flags in (0, _native.HG_TWO_PASS, _native.HG_FORCE_STREAM):
                 ops.aggregate(plan, X.to(cuda_device), s1=hg.degE, a_out=hg.degV, out=out, flags=flags)
                 assert orc.rel_err(_np(out), want) < TOL or np.abs(want).max() == 0, (len(members), N, ngs, F, flags)
             plan.check()

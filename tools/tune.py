@@ -28,7 +28,7 @@ plan = ops.get_plan(hg.group_key, hg.group_row, hg.group_start, hg.group_end, hg
 W = torch.ones(M, device=dev)
 flags = _native.HG_TWO_PASS if args.two_pass else (_native.HG_FORCE_FUSED if args.force_fused else (_native.HG_FORCE_PULL if args.force_pull else (_native.HG_FORCE_STREAM if args.force_stream else (_native.HG_FORCE_RING if args.force_ring else (_native.HG_FORCE_FSTREAM if args.force_fstream else 0)))))
 TUNED = set()
-KNOBS = ("HGEF_ST_FUSED", "HGEF_ST_L", "HGEF_ST_LAG", "HGEF_ST_SLAB", "HGEF_ST_CTAS", "HGEF_ST_ONLY", "HGEF_ST_OCC", "HGEF_ST_CS", "HGEF_ST_SW", "HGEF_ST_PIPE")
+KNOBS = ()   # (all knobs go through hg_tune_set: "st_l=64,st_occ=4;..."; lab forms need HGEF_B200_LIB=hypergef_b200/libhgef_b200_lab.so)
 for cfg in (args.sweep.split(";") if args.sweep else [""]):
     for k in (KNOBS if args.sweep else ()):
         os.environ.pop(k, None)
@@ -36,11 +36,8 @@ for cfg in (args.sweep.split(";") if args.sweep else [""]):
     TUNED.clear()
     for kv in filter(None, cfg.split(",")):
         k, v = kv.split("=")
-        if k.startswith("ring") or k.startswith("fs_") or k.startswith("st_") or k == "fstream":     # hg_tune_set knobs
-            ops.tune(**{k: int(v)})
-            TUNED.add(k)
-        else:
-            os.environ[k if k.startswith("HGEF_") else "HGEF_ST_" + k] = v
+        ops.tune(**{k: int(v)})
+        TUNED.add(k)
     out = []
     for F in [int(f) for f in args.features.split(",")]:
         X = torch.randn(N, F, device=dev); Y = torch.empty(N, F, device=dev)

@@ -61,6 +61,8 @@ SIGNATURES = {
     "hg_aggr_mean": [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _int, _vp],
     "hg_aggr_max_forward": [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _int, _vp],
     "hg_aggr_max_backward": [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _int, _vp],
+    "hg_plan_max_forward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp],
+    "hg_plan_max_backward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp],
     "hg_weight_grad": [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _int, _vp],
 }
 

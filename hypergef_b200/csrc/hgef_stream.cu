@@ -510,7 +510,7 @@ int ensure_xe(hgPlan *plan, int F, cudaStream_t s) {
 
 // Launch geometry.  Defaults from the sweeps in profiles/; every one can be overridden through hg_tune_set
 // (st_slab, st_sw, st_l, st_ctas, st_occ, st_pipe, st_cs, st_pdl, st_only) -- read from a table, not the environment.
-int launch_stream(hgPlan *p, const dev::Args &a, cudaStream_t s) {
+int launch_stream_stages(hgPlan *p, const dev::Args &a, int stages, cudaStream_t s) {
   const int F = a.F;
   if (int rc = ensure_xe(p, F, s)) return rc;
   StreamCfg cfg{};
@@ -545,7 +545,7 @@ int launch_stream(hgPlan *p, const dev::Args &a, cudaStream_t s) {
   const int bpi = cfg.k0 * ksub;
   const bool has_win = a.a_in != nullptr;
 
-  if (p->nheavy_segs > 0) {
+  if (p->nheavy_segs > 0 && (stages & 1)) {
     zero_rows_kernel<<<(unsigned)ceil_div<int64_t>(p->nheavy_segs * 32, 256), 256, 0, s>>>(
         p->nheavy_segs, p->heavy_segs, p->seg_edge, p->xe, F);
     HG_CUDA_TRY(cudaGetLastError());
@@ -566,16 +566,19 @@ int launch_stream(hgPlan *p, const dev::Args &a, cudaStream_t s) {
   // dependent launch: its CTAs are scheduled while stage A drains and wait (griddepcontrol.wait) for A's
   // memory to be flushed before they touch Xe
   const int only = tune_get("st_only", 0);   // timing: 1 = stage A, 2 = stage B
-  if (only != 2) {
-    sa.stage = 0; sa.nitem = GA; sa.ctrl = p->st_ctrl; sa.pdl = (cfg.pdl && only == 0) ? 1 : 0;
+  if (only == 1 || only == 2) stages &= only;
+  if (stages & 1) {
+    sa.stage = 0; sa.nitem = GA; sa.ctrl = p->st_ctrl; sa.pdl = (cfg.pdl && stages == 3) ? 1 : 0;
     ++p->kernels_launched;
     if (int rc = dispatch(p, sa, cfg, 0, has_win, s)) return rc;
   }
-  if (only == 1) return HG_OK;
-  sa.stage = 1; sa.nitem = GB; sa.ctrl = p->st_ctrl + kCtrlHdr; sa.pdl = (cfg.pdl && only == 0) ? 1 : 0;
+  if (!(stages & 2)) return HG_OK;
+  sa.stage = 1; sa.nitem = GB; sa.ctrl = p->st_ctrl + kCtrlHdr; sa.pdl = (cfg.pdl && stages == 3) ? 1 : 0;
   ++p->kernels_launched;
   return dispatch(p, sa, cfg, 1, false, s);
 }
+
+int launch_stream(hgPlan *p, const dev::Args &a, cudaStream_t s) { return launch_stream_stages(p, a, 3, s); }
 
 // ---- feature lengths that are not a multiple of 4: the same kernels on rows padded to the next multiple
 namespace {

@@ -21,6 +21,9 @@ constexpr int kFlagOff = 32, kDbgOff = 40, kCntOff = 64;
 int tune_get(const char *name, int dflt);
 
 int ensure_xe(hgPlan *plan, int F, cudaStream_t s);
+// stream form, selected stages: 1 = stage A (X -> plan->xe), 2 = stage B (plan->xe -> Y), 3 = both
+int launch_stream_stages(hgPlan *p, const dev::Args &a, int stages, cudaStream_t s);
+bool stream_available(const hgPlan *plan, int F, bool force);
 int stream_build_runs(hgPlan *p, int L0, int32_t **runA, int64_t *nrunA, int32_t **runB, int64_t *nrunB, cudaStream_t s);
 
 // merged A / B / discard ticket order over items of `bpi` fine runs (hgef_ring.cu), cached in the plan;

@@ -510,9 +510,14 @@ class _MaxF1(torch.autograd.Function):
         out = torch.empty_like(X)
         record = torch.empty((M, X.shape[1]), dtype=torch.int32, device=X.device)
         dev, stream = _dev_stream(X)
-        _native.call("hg_aggr_max_forward", N, M, csrptr_t.data_ptr(), indices_t.data_ptr(), X.data_ptr(),
-                     _ptr(s1), _ptr(s2), _ptr(a_out), out.data_ptr(), record.data_ptr(), X.shape[1], 0,
-                     dev, stream)
+        if MEAN_BALANCED and M > 0 and indices_t.numel() > 0:
+            plan = _csr_plan(csrptr_t, indices_t, N, M)
+            _native.call("hg_plan_max_forward", plan.handle, csrptr_t.data_ptr(), X.data_ptr(), _ptr(s1), _ptr(s2),
+                         _ptr(a_out), out.data_ptr(), record.data_ptr(), X.shape[1], stream)
+        else:
+            _native.call("hg_aggr_max_forward", N, M, csrptr_t.data_ptr(), indices_t.data_ptr(), X.data_ptr(),
+                         _ptr(s1), _ptr(s2), _ptr(a_out), out.data_ptr(), record.data_ptr(), X.shape[1], 0,
+                         dev, stream)
         ctx.args = (csrptr_t, indices_t, s1, a_out, s2, N, M, record)
         ctx.mark_non_differentiable(record)
         return out, record
@@ -523,9 +528,14 @@ class _MaxF1(torch.autograd.Function):
         G = grad_out.contiguous()
         dX = torch.empty_like(G)
         dev, stream = _dev_stream(G)
-        _native.call("hg_aggr_max_backward", N, M, csrptr_t.data_ptr(), indices_t.data_ptr(), G.data_ptr(),
-                     _ptr(s1), _ptr(s2), _ptr(a_out), record.data_ptr(), dX.data_ptr(), G.shape[1], 0,
-                     dev, stream)
+        if MEAN_BALANCED and M > 0 and indices_t.numel() > 0:
+            plan = _csr_plan(csrptr_t, indices_t, N, M)
+            _native.call("hg_plan_max_backward", plan.handle, csrptr_t.data_ptr(), G.data_ptr(), _ptr(s1), _ptr(s2),
+                         _ptr(a_out), record.data_ptr(), dX.data_ptr(), G.shape[1], stream)
+        else:
+            _native.call("hg_aggr_max_backward", N, M, csrptr_t.data_ptr(), indices_t.data_ptr(), G.data_ptr(),
+                         _ptr(s1), _ptr(s2), _ptr(a_out), record.data_ptr(), dX.data_ptr(), G.shape[1], 0,
+                         dev, stream)
         return None, None, dX, None, None, None
 
 

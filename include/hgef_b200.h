@@ -234,6 +234,17 @@ HG_API int hg_aggr_max_backward(int64_t num_nodes, int64_t num_edges, const int3
                                 const float *d_s2, const float *d_a_out, const int32_t *d_record,
                                 float *d_dX, int32_t F, int32_t flags, int device, void *stream);
 
+/* The same max op over a PLAN (balanced): one warp per balancer segment, the segments of a split hyperedge meet in a
+ * packed (value, vertex id) atomicMax, the second stage is the stream form's stage B (every Y row written once).
+ * d_t_indptr is only used when the plan cannot serve the call (non-canonical groups, F % 4 != 0): then the
+ * un-balanced kernels above run.  Backward = hgnnaggr_max_bp_cuda's formula (hgnnaggr_cuda.cu:165-208). */
+HG_API int hg_plan_max_forward(hgPlan *plan, const int32_t *d_t_indptr, const float *d_X, const float *d_s1,
+                               const float *d_s2, const float *d_a_out, float *d_Y, int32_t *d_record,
+                               int32_t F, void *stream);
+HG_API int hg_plan_max_backward(hgPlan *plan, const int32_t *d_t_indptr, const float *d_G, const float *d_s1,
+                                const float *d_s2, const float *d_a_out, const int32_t *d_record,
+                                float *d_dX, int32_t F, void *stream);
+
 /* Gradient of the hyperedge weight W (the reference op returns none, hgnnaggr.cc:62-63;
  * un-scaled host reference include/util/check.cuh:116-143):
  *   dW[e] = s1[e] * sum_k (sum_{u in e} a_in[u] X[u,k]) * (sum_{v in e} a_out[v] G[v,k]) */

@@ -139,3 +139,22 @@ def test_matches_reference_gpu_kernels(shape, F, cuda_device):
                             hg.num_edges)
         got = ops.aggregate(plan, X, flags=flags)
         assert ((got - ref).abs().max().item() / scale) < TOL, flags
+
+
+def test_partitioned_aggregation_over_nccl_matches_single_gpu(cuda_device):
+    """Vertex / hyperedge partitioned path over NCCL (needs >= 2 visible GPUs; skipped on a one-GPU box): every
+    rank's block of Y against the single-GPU kernel on the same replicated inputs, through torchrun."""
+    import json, os, subprocess, sys
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs at least two visible GPUs")
+    world = 4 if ngpu >= 4 else 2
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", "29517", os.path.join(root, "tools", "run_partition.py"), "--scale", "0.004", "--F", "64", "--iters", "2",
+           "--check", "1"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=root)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+    out = json.loads(line)
+    assert out["world"] == world and out["max_rel_err_vs_single_gpu"] < TOL, out

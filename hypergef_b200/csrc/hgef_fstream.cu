@@ -49,6 +49,9 @@ struct FArgs {
   int32_t pol_x, pol_xe_w, pol_y;
   int32_t batch;                    // tickets claimed per atomic; finished items are published once per batch
   int32_t debug;                    // bit 0: no release fence, bit 1: no dependency waits (timing experiments only)
+  const int4 *tabs;                 // split-role form: item records per kind and index
+  int32_t GC, maxlead, doff;        // discard items; how far (in items) stage A may run ahead of the claimed B items;
+                                    // how many B blocks later a block's discards are attempted
 };
 
 __device__ __forceinline__ int ld_relaxed(const int *p) {
@@ -363,6 +366,210 @@ __global__ void __launch_bounds__(kThreads, MINB) fstream_kernel(const __grid_co
 }
 
 
+
+// ---------------------------------------------------------------------------------------------------
+// SPLIT-ROLE form.  The merged ticket order above makes every warp wait for whatever its next ticket needs; a
+// lag that avoids the waits is longer than the L2 retains.  Here the CTAs of one launch take FIXED roles (even
+// blocks: stage A, odd blocks: stage B + discards), each role with its own ticket counter, and the distance
+// between the two is bounded from both sides: a B item waits until the A blocks it needs are complete (it
+// cannot run ahead), an A item waits while it is more than `maxlead` items ahead of the completed B prefix (it
+// cannot run away).  maxlead >= the largest lead any B item needs (computed from the graph, RingSched::lead), so
+// the A items the oldest unfinished B item needs always pass the throttle: no deadlock.  No warp ever claims an
+// item of the other role, so there is no contended "is it ready?" race.
+// ---------------------------------------------------------------------------------------------------
+template <int SW, int VPL, bool HAS_WIN, int MINB, bool PIPE>
+__global__ void __launch_bounds__(kThreads, MINB) dstream_kernel(const __grid_constant__ FArgs fa) {
+  using G = SGeo<SW, VPL, 8>;
+  static_assert(G::kSub <= 4, "an item record carries three split points");
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / SW, sl = lane % SW;
+  const bool roleB = (blockIdx.x & 1) != 0;
+  const uint64_t pol_x = make_policy(fa.pol_x), pol_xe_w = make_policy(fa.pol_xe_w), pol_y = make_policy(fa.pol_y);
+  const int GA = fa.GA, GB = fa.GB, GC = fa.GC;
+  const int nblk = fa.nblkA + fa.nblkB;
+  int wmA = 0, wmB = 0, slabA = -1, slabB = -1;   // completed prefix blocks of the slab last looked at
+  bool gave_up = false;
+
+  // blocks [0, need) of `kind` of `slab` complete?  waits (bounded) until they are; one acquire fence at the end
+  auto wait_blocks = [&](int kind, int slab, int need) {
+    int &w = kind == 0 ? wmA : wmB;
+    int &ws = kind == 0 ? slabA : slabB;
+    if (slab != ws) { ws = slab; w = 0; }
+    if (w >= need || (fa.debug & 2)) return;
+    const int G_ = kind == 0 ? GA : GB;
+    const int *cnt = fa.ctrl + kCntOff + (int64_t)slab * nblk + (kind == 0 ? 0 : fa.nblkA);
+    unsigned spins = 0;
+    while (w < need && !gave_up) {
+      const int b = w + lane;
+      bool done = true;
+      if (b < need) done = ld_relaxed(cnt + b) == min(kBlk, G_ - b * kBlk);
+      const unsigned m = __ballot_sync(kFull, done);
+      w = min(need, w + (m == kFull ? 32 : __ffs(~m) - 1));
+      if (w < need && m != kFull) {
+        __nanosleep(100);
+        ++spins;
+        if (spins > (1u << 20) || ((spins & 255u) == 0 && ld_relaxed(fa.ctrl + kFlagOff) != 0)) {
+          if (lane == 0) atomicExch(fa.ctrl + kFlagOff, 1);
+          gave_up = true;
+        }
+      }
+    }
+    asm volatile("fence.acquire.gpu;" ::: "memory");
+  };
+  auto publish = [&](int kind, int slab, int idx) {
+    __syncwarp();
+    if (lane == 0) {
+      if (!(fa.debug & 1)) asm volatile("fence.release.gpu;" ::: "memory");
+      red_inc_relaxed(fa.ctrl + kCntOff + slab * nblk + (kind == 0 ? 0 : fa.nblkA) + idx / kBlk);
+    }
+  };
+  auto bounds = [&](const int4 &ia, const int4 &ib, int32_t &ps, int32_t &pe) {
+    ps = ia.x; pe = ia.y;
+    if (G::kSub == 2) { ps = sub == 0 ? ia.x : ib.x; pe = sub == 0 ? ib.x : ia.y; }
+    if (G::kSub == 4) {
+      ps = sub == 0 ? ia.x : (sub == 1 ? ib.x : (sub == 2 ? ib.y : ib.z));
+      pe = sub == 0 ? ib.x : (sub == 1 ? ib.y : (sub == 2 ? ib.z : ia.y));
+    }
+  };
+
+  if (!roleB) {
+    // ------------------------------ stage A warps ------------------------------
+    const int total = GA * fa.nslab;
+    int64_t seenB = 0;                    // B tickets seen claimed
+    int t_raw = 0;
+    if (lane == 0) t_raw = atomicAdd(fa.ctrl, 1);
+    for (;;) {
+      const int t = __shfl_sync(kFull, t_raw, 0);
+      if (t >= total) break;
+      if (lane == 0) t_raw = atomicAdd(fa.ctrl, 1);          // the next ticket: in flight while this item streams
+      const int slab = fa.nslab > 1 ? t / GA : 0;
+      const int idx = t - slab * GA;
+      const int4 ia = __ldg(fa.tabs + 2 * idx);
+      int4 ib = make_int4(0, 0, 0, 0);
+      if (G::kSub > 1) ib = __ldg(fa.tabs + 2 * idx + 1);
+      // throttle: not more than maxlead items ahead of the B items CLAIMED so far (the B ticket counter; relaxed
+      // polls).  B items are claimed in order and a claimed B item only ever waits for A items below its own index
+      // + the graph's lead <= maxlead, which pass this test: no deadlock.
+      if (!(fa.debug & 2)) {
+        const int64_t tb_need = (int64_t)slab * GB + idx - fa.maxlead;
+        if (tb_need > seenB) {
+          unsigned spins = 0;
+          for (;;) {
+            int v = 0;
+            if (lane == 0) v = ld_relaxed(fa.ctrl + kNextB);
+            seenB = __shfl_sync(kFull, v, 0);
+            if (seenB >= tb_need || gave_up) break;
+            __nanosleep(200);
+            if (++spins > (1u << 20) || ((spins & 255u) == 0 && ld_relaxed(fa.ctrl + kFlagOff) != 0)) {
+              if (lane == 0) atomicExch(fa.ctrl + kFlagOff, 1);
+              gave_up = true;
+            }
+          }
+        }
+      }
+      const int col0 = slab * fa.slabF;
+      const int Fs = min(fa.slabF, fa.F - col0);
+      int32_t ps, pe;
+      bounds(ia, ib, ps, pe);
+      stream_run<0, SW, VPL, 8, HAS_WIN, PIPE>(fa, ps, pe, col0, Fs, sl, pol_x, pol_xe_w);
+      publish(0, slab, idx);
+    }
+  } else {
+    // ------------------------------ stage B warps (and the discards) ------------------------------
+    const int total = GB * fa.nslab;
+    const int4 *tabB = fa.tabs + 2 * GA, *tabC = fa.tabs + 2 * (GA + GB);
+    int t_raw = 0;
+    if (lane == 0) t_raw = atomicAdd(fa.ctrl + kNextB, 1);
+    for (;;) {
+      const int t = __shfl_sync(kFull, t_raw, 0);
+      if (t >= total) break;
+      if (lane == 0) t_raw = atomicAdd(fa.ctrl + kNextB, 1);
+      const int slab = fa.nslab > 1 ? t / GB : 0;
+      const int idx = t - slab * GB;
+      const int4 ia = __ldg(tabB + 2 * idx);
+      int4 ib = make_int4(0, 0, 0, 0);
+      if (G::kSub > 1) ib = __ldg(tabB + 2 * idx + 1);
+      if (ia.w > 0) wait_blocks(0, slab, ia.w);
+      const int col0 = slab * fa.slabF;
+      const int Fs = min(fa.slabF, fa.F - col0);
+      if (fa.niso > 0) {   // this item's share of the vertices that no hyperedge touches
+        const int i0 = (int)((int64_t)fa.niso * idx / GB), i1 = (int)((int64_t)fa.niso * (idx + 1) / GB);
+        for (int i = i0 + sub; i < i1; i += G::kSub) {
+          float *yp = fa.out[1] + (int64_t)__ldg(fa.iso + i) * fa.F + col0;
+#pragma unroll
+          for (int v = 0; v < VPL; ++v)
+            if (sl * 4 + v * G::kStride < Fs) st_row_hint(yp + sl * 4 + v * G::kStride, make_float4(0.f, 0.f, 0.f, 0.f), pol_y);
+        }
+      }
+      int32_t ps, pe;
+      bounds(ia, ib, ps, pe);
+      stream_run<1, SW, VPL, 8, HAS_WIN, PIPE>(fa, ps, pe, col0, Fs, sl, 0, pol_y);
+      if (fa.track_b) publish(1, slab, idx);
+      // discards: the warp that finishes the LAST item of B block k looks after discard item k - doff (the rows whose
+      // last reader lies in that earlier block) -- exactly one attempt per discard item, no contended claim.  The
+      // attempt is non-blocking: if the B blocks up to it are not all complete yet, the item is skipped (a discard is an
+      // optimisation: a skipped one costs a write-back, not correctness).  A warp waiting here would sit on its
+      // prefetched B ticket, which the block it waits for may contain.
+      if (GC > 0 && (idx % kBlk == kBlk - 1 || idx == GB - 1)) {
+        const int ci = idx / kBlk - fa.doff;
+        if (ci >= 0) {
+          if (slab != slabB) { slabB = slab; wmB = 0; }
+          const int *cnt = fa.ctrl + kCntOff + (int64_t)slab * nblk + fa.nblkA;
+          for (int pass = 0; pass < 64 && wmB < ci + 1; ++pass) {     // polling passes over the missing blocks
+            const int bb = wmB + lane;
+            bool done = true;
+            if (bb < ci + 1) done = ld_relaxed(cnt + bb) == min(kBlk, GB - bb * kBlk);
+            const unsigned m = __ballot_sync(kFull, done);
+            const int adv = m == kFull ? 32 : __ffs(~m) - 1;
+            wmB = min(ci + 1, wmB + adv);
+            if (adv < 32) break;
+          }
+          if (wmB >= ci + 1) {
+            asm volatile("fence.acquire.gpu;" ::: "memory");
+            const int4 ic = __ldg(tabC + 2 * ci);
+            const int lines = Fs >> 5;
+            const int totl = (ic.y - ic.x) * lines;
+            for (int x = lane; x < totl; x += 32) {
+              const int r = x / lines, l = x - r * lines;
+              const int32_t e = __ldg(fa.dperm + ic.x + r);
+              const float *p = fa.in[1] + (int64_t)e * fa.F + col0 + l * 32;
+              asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int SW, int VPL, bool HAS_WIN>
+int launch_split(hgPlan *p, const FArgs &fa, bool pipe, int occ, cudaStream_t s) {
+  void (*kern)(const FArgs) = nullptr;
+  if (occ <= 2) kern = pipe ? dstream_kernel<SW, VPL, HAS_WIN, 2, true> : dstream_kernel<SW, VPL, HAS_WIN, 2, false>;
+  else kern = pipe ? dstream_kernel<SW, VPL, HAS_WIN, 3, true> : dstream_kernel<SW, VPL, HAS_WIN, 3, false>;
+  int per_sm = 0;
+  HG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0));
+  if (per_sm < 1) per_sm = 1;
+  if (occ < per_sm) per_sm = occ < 1 ? 1 : occ;
+  int64_t grid = (int64_t)p->sm_count * per_sm;
+  if (grid < 2) grid = 2;
+  grid &= ~int64_t(1);                       // both roles get the same number of CTAs
+  // every CTA must be resident: the two roles wait for each other
+  kern<<<(unsigned)grid, kThreads, 0, s>>>(fa);
+  HG_CUDA_TRY(cudaGetLastError());
+  return HG_OK;
+}
+
+int dispatch_split(hgPlan *p, const FArgs &fa, int sw, int vpl, bool pipe, bool has_win, int occ, cudaStream_t s) {
+#define HG_CASE(SW_, VPL_)                                                                                   \
+  if (sw == SW_ && vpl == VPL_)                                                                              \
+    return has_win ? launch_split<SW_, VPL_, true>(p, fa, pipe, occ, s) : launch_split<SW_, VPL_, false>(p, fa, pipe, occ, s);
+  HG_CASE(8, 1) HG_CASE(8, 2) HG_CASE(8, 4) HG_CASE(16, 1) HG_CASE(16, 2) HG_CASE(16, 4)
+  HG_CASE(32, 1) HG_CASE(32, 2) HG_CASE(32, 4)
+#undef HG_CASE
+  return set_error(HG_EINVAL, "split-role stream: no kernel for sub-warp %d x %d vectors", sw, vpl);
+}
+
 struct FCfg { int sw, vpl, occ, kv; bool pipe; };
 
 template <int SW, int VPL, bool HAS_WIN>
@@ -443,12 +650,14 @@ int launch_fstream(hgPlan *p, const dev::Args &a, cudaStream_t s) {
   const int bpi = k0 * ksub;
   const int warps = p->sm_count * (ctas > 0 ? ctas : cfg.occ) * kWarpsPerBlock;
   int lagB = tune_get("fs_lag_b", -1), lagC = tune_get("fs_lag_c", -1);
-  const int batch_t = tune_get("fs_batch", 4) < 1 ? 1 : tune_get("fs_batch", 4);
+  const int batch_t = 1;
   if (lagB < 0) lagB = warps * batch_t;   // every warp may hold a batch of unfinished items
   if (lagC < 0) lagC = warps * batch_t;
   // rows can be discarded line by line only if they are made of whole 128-byte lines
   const int discard = (F % 32 == 0 && tune_get("fs_discard", 1) != 0) ? 1 : 0;
 
+  const bool split = tune_get("fs_split", 1) != 0;
+  if (split) { lagB = 0; lagC = 0; }         // the merged order is not used: one cached table set per item size
   hgPlan::RingSched *sc = nullptr;
   if (int rc = fused_get_sched(p, bpi, lagB, lagC, nslab, discard, ksub, s, &sc)) return rc;
   if (p->nheavy_segs > 0) {
@@ -472,12 +681,22 @@ int launch_fstream(hgPlan *p, const dev::Args &a, cudaStream_t s) {
   fa.pol_x = tune_get("fs_pol_x", kPolFirst);
   fa.pol_xe_w = tune_get("fs_pol_xe_w", kPolLast);
   fa.pol_y = tune_get("fs_pol_y", kPolFirst);
-  fa.batch = tune_get("fs_batch", 4);
-  if (fa.batch < 1) fa.batch = 1;
-  if (fa.batch > 32) fa.batch = 32;
+  // (claiming and publishing tickets in batches of 2..32 was measured: no gain, and one configuration timed out on the
+  //  Walmart shape -- profiles/r02_fstream_autonomous_warps_rejected.txt; the code path stays for the record, off)
+  fa.batch = 1;
   fa.debug = tune_get("fs_debug", 0);
   p->rg_last_ctrl = sc->ctrl;
   ++p->kernels_launched;
+  if (split) {
+    fa.tabs = sc->tabs; fa.GC = sc->GC;
+    const int extra = tune_get("fs_lead", -1);
+    // stage A may run this many items ahead of the completed B prefix: what the graph needs + a margin of one
+    // front of warps (so that neither role waits in the steady state)
+    fa.maxlead = sc->lead + (extra >= 0 ? extra : warps / 2) + 2 * kBlk;
+    const int doff_t = tune_get("fs_doff", -1);
+    fa.doff = doff_t >= 0 ? doff_t : (warps / 2 + kBlk - 1) / kBlk + 8;   // ~ the B blocks in flight
+    return dispatch_split(p, fa, cfg.sw, cfg.vpl, cfg.pipe, a.a_in != nullptr, cfg.occ, s);
+  }
   return dispatch(p, fa, cfg, a.a_in != nullptr, ctas, s);
 }
 

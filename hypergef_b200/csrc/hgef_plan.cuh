@@ -49,6 +49,8 @@ struct hgPlan {
   struct RingSched {
     int bpi, lagB, lagC, nslab, discard, ksub;
     int32_t GA, GB, GC, nblkA, nblkB, nitem;
+    int4 *tabs;                   // the same records per kind and index: A at [0, 2 GA), B, then discard items
+    int32_t lead;                 // max over B items of (A items it needs - its own index): the bound of the split-role form
     int4 *items;                  // per ticket two words: {first position, end position, kind | index << 2, blocks needed},
                                   //   {sub-stream split points 1..3, 0}
     int32_t *ctrl;                // kCtrlHdr + nslab * (nblkA + nblkB) words

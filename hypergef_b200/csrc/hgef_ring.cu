@@ -695,6 +695,18 @@ __global__ void sched_items_kernel(int32_t n, const int32_t *__restrict__ vals, 
   items[2 * k + 1] = sp;
 }
 
+__global__ void sched_tabs_kernel(int32_t n, const int4 *__restrict__ items, int32_t GA, int32_t GB, int4 *__restrict__ tabs,
+                                  int32_t *__restrict__ lead) {
+  const int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int4 a = items[2 * k], b = items[2 * k + 1];
+  const int32_t kind = a.z & 3, idx = a.z >> 2;
+  const int32_t base = kind == kKindA ? 0 : (kind == kKindB ? GA : GA + GB);
+  tabs[2 * (base + idx)] = a;
+  tabs[2 * (base + idx) + 1] = b;
+  if (kind == kKindB) atomicMax(lead, a.w * kBlk - idx);
+}
+
 int build_discard(hgPlan *p, cudaStream_t s) {
   if (p->rg_ready) return HG_OK;
   const int64_t M = p->num_edges, Z = p->nnz;
@@ -730,7 +742,7 @@ int fused_get_sched(hgPlan *p, int bpi, int lagB, int lagC, int nslab, int disca
   }
   if (p->rg_nsched == hgPlan::kMaxSched) {   // recycle the oldest entry
     HG_CUDA_TRY(cudaStreamSynchronize(s));
-    cudaFree(p->rg_sched[0].items); cudaFree(p->rg_sched[0].ctrl);
+    cudaFree(p->rg_sched[0].items); cudaFree(p->rg_sched[0].ctrl); cudaFree(p->rg_sched[0].tabs);
     for (int i = 1; i < p->rg_nsched; ++i) p->rg_sched[i - 1] = p->rg_sched[i];
     --p->rg_nsched;
   }
@@ -764,6 +776,14 @@ int fused_get_sched(hgPlan *p, int bpi, int lagB, int lagC, int nslab, int disca
                                              (int32_t)p->rg_nrunB, need_blk.p, p->rg_dlast, (int32_t)p->num_edges, c.GC,
                                              c.items);
   HG_CUDA_TRY(cudaGetLastError());
+  // per-kind tables (split-role form) and the largest lead a B item needs: need_blk * kBlk - its index
+  if (int rc = dev_alloc(&c.tabs, (size_t)c.nitem * 2)) return rc;
+  DevBuf<int32_t> lead;
+  HG_CUDA_TRY(lead.alloc(1));
+  HG_CUDA_TRY(cudaMemsetAsync(lead.p, 0, sizeof(int32_t), s));
+  sched_tabs_kernel<<<GRID(c.nitem), 0, s>>>(c.nitem, c.items, c.GA, c.GB, c.tabs, lead.p);
+  HG_CUDA_TRY(cudaGetLastError());
+  HG_CUDA_TRY(cudaMemcpyAsync(&c.lead, lead.p, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   HG_CUDA_TRY(cudaStreamSynchronize(s));
   p->rg_sched[p->rg_nsched] = c;
   *out = &p->rg_sched[p->rg_nsched++];
@@ -794,7 +814,7 @@ int launch_vpl(const RingArgs &ra, bool has_win, unsigned grid, unsigned threads
 
 void ring_free(hgPlan *p) {
   cudaFree(p->rg_dperm); cudaFree(p->rg_dlast); cudaFree(p->rg_runA); cudaFree(p->rg_runB);
-  for (int i = 0; i < p->rg_nsched; ++i) { cudaFree(p->rg_sched[i].items); cudaFree(p->rg_sched[i].ctrl); }
+  for (int i = 0; i < p->rg_nsched; ++i) { cudaFree(p->rg_sched[i].items); cudaFree(p->rg_sched[i].ctrl); cudaFree(p->rg_sched[i].tabs); }
   p->rg_nsched = 0;
 }
 

@@ -248,7 +248,16 @@ __global__ void __launch_bounds__(kThreads, MINB) stream_kernel(const StreamArgs
       c_src = n_src;
       c_dst = n_dst;
     }
-
+  }
+  // the last warp of the grid to leave resets the ticket counter for the next launch (ctrl[2] counts leavers),
+  // so a call needs no memset between its launches
+  if (lane == 0) {
+    const int nw = (int)(gridDim.x * (blockDim.x >> 5));
+    if (atomicAdd(sa.ctrl + 2, 1) == nw - 1) {
+      sa.ctrl[0] = 0;
+      sa.ctrl[2] = 0;
+      __threadfence();
+    }
   }
 }
 

@@ -15,7 +15,7 @@ constexpr int kBlk = 8;      // items per completion counter
 constexpr int kCtrlHdr = 8;  // stream form: ctrl[0] ticket counter, ctrl[1] give-up flag, ctrl[8..] completion counts
 // fused forms: the ticket counter (hammered by every warp), the give-up flag and the completion counters (polled
 // by waiting warps) live on separate 128-byte lines -- same-line traffic slows the ticket atomics
-constexpr int kFlagOff = 32, kDbgOff = 40, kCntOff = 64;
+constexpr int kFlagOff = 32, kDbgOff = 40, kNextB = 64, kNextC = 96, kCntOff = 128;
 
 // process-wide tuning table (hg_tune_set); -1 / absent = the built-in default
 int tune_get(const char *name, int dflt);

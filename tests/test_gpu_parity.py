@@ -146,8 +146,7 @@ def test_plan_sees_heavy_hyperedges_and_schedules_agree(cuda_device):
     want = orc.c_aggr_groups(d["group_key"], d["group_row"], d["group_start"], d["group_end"], d["H_T_colind"],
                              d["X"], s1=d["degE"], a_out=d["degV"])
     assert orc.rel_err(_np(Y1), want) < TOL and orc.rel_err(_np(Y2), want) < TOL
-    for flag in (_native.HG_FORCE_SCALAR, _native.HG_TWO_PASS, _native.HG_FORCE_FUSED, _native.HG_FORCE_PULL,
-                 _native.HG_FORCE_STREAM):
+    for flag in (_native.HG_FORCE_SCALAR, _native.HG_TWO_PASS, _native.HG_FORCE_STREAM):
         Y3 = ops.aggregate(plan, X, s1=hg.degE, a_out=hg.degV, flags=flag)
         assert orc.rel_err(_np(Y3), want) < TOL
     plan.check()

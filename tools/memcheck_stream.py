@@ -16,13 +16,12 @@ for shape, reps in (("pubmed", 1), ("walmart", 1)):
     for F in (4, 32, 100, 128, 256, 640):
         X = torch.randn(hg.num_nodes, F, device=dev)
         ref = ops.aggregate(plan, X, s1=hg.degE, s2=W, a_out=hg.degV, flags=_native.HG_TWO_PASS)
-        for env in ({}, {"HGEF_ST_FUSED": "1"}, {"HGEF_ST_L": "16"}, {"HGEF_ST_PIPE": "0"}):
-            for k in ("HGEF_ST_FUSED", "HGEF_ST_L", "HGEF_ST_PIPE"):
-                os.environ.pop(k, None)
-            os.environ.update(env)
+        for knobs in ({}, {"st_pdl": 0}, {"st_l": 16}, {"st_pipe": 0}):
+            ops.tune(st_pdl=None, st_l=None, st_pipe=None)
+            ops.tune(**knobs)
             out = ops.aggregate(plan, X, s1=hg.degE, s2=W, a_out=hg.degV, flags=_native.HG_FORCE_STREAM)
             out_t = ops.aggregate(plan, X, s1=hg.degE, s2=W, a_in=hg.degV, flags=_native.HG_FORCE_STREAM)
             err = ((out - ref).abs().max() / ref.abs().max()).item()
-            assert err < 1e-5, (shape, F, env, err)
+            assert err < 1e-5, (shape, F, knobs, err)
         plan.check()
     print("ok", shape, hg.num_nodes, plan.nheavy_edges, flush=True)

@@ -542,6 +542,189 @@ __global__ void __launch_bounds__(kThreads, MINB) dstream_kernel(const __grid_co
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// ALTERNATING form.  Every warp takes an A item, then a B item, then an A item ... from the two ticket counters of the
+// split-role tables.  A items never wait.  A warp HOLDS its B ticket until the A blocks the item needs are complete
+// and meanwhile keeps taking A items (it never polls while there is A work), so stage A runs ahead of stage B by
+// exactly what the graph needs plus the items in flight, with no throttle and no lag parameter.  Only when the A
+// tickets are exhausted does a warp wait for its B item -- and then every A item is in the hands of a warp that is
+// streaming it, so the wait ends: no deadlock, and not every CTA has to be resident.
+// ---------------------------------------------------------------------------------------------------
+template <int SW, int VPL, bool HAS_WIN, int MINB, bool PIPE>
+__global__ void __launch_bounds__(kThreads, MINB) astream_kernel(const __grid_constant__ FArgs fa) {
+  using G = SGeo<SW, VPL, 8>;
+  static_assert(G::kSub <= 4, "an item record carries three split points");
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / SW, sl = lane % SW;
+  const uint64_t pol_x = make_policy(fa.pol_x), pol_xe_w = make_policy(fa.pol_xe_w), pol_y = make_policy(fa.pol_y);
+  const int GA = fa.GA, GB = fa.GB, GC = fa.GC;
+  const int nblk = fa.nblkA + fa.nblkB;
+  const int totalA = GA * fa.nslab, totalB = GB * fa.nslab;
+  const int4 *tabB = fa.tabs + 2 * GA, *tabC = fa.tabs + 2 * (GA + GB);
+  int wmA = 0, wmB = 0, slabA = -1, slabB = -1;   // completed prefix blocks of the slab last looked at
+  bool gave_up = false;
+
+  // one pass over the completion counters of blocks [w, need): how far is the prefix complete?  (non-blocking)
+  auto scan_blocks = [&](int kind, int slab, int need) -> bool {
+    int &w = kind == 0 ? wmA : wmB;
+    int &ws = kind == 0 ? slabA : slabB;
+    if (slab != ws) { ws = slab; w = 0; }
+    if (fa.debug & 2) return true;
+    const int G_ = kind == 0 ? GA : GB;
+    const int *cnt = fa.ctrl + kCntOff + (int64_t)slab * nblk + (kind == 0 ? 0 : fa.nblkA);
+    while (w < need) {
+      const int b = w + lane;
+      bool done = true;
+      if (b < need) done = ld_relaxed(cnt + b) == min(kBlk, G_ - b * kBlk);
+      const unsigned m = __ballot_sync(kFull, done);
+      const int adv = m == kFull ? 32 : __ffs(~m) - 1;
+      w = min(need, w + adv);
+      if (adv < 32) break;
+    }
+    return w >= need;
+  };
+  auto publish = [&](int kind, int slab, int idx) {
+    __syncwarp();
+    if (lane == 0) {
+      if (!(fa.debug & 1)) asm volatile("fence.release.gpu;" ::: "memory");
+      red_inc_relaxed(fa.ctrl + kCntOff + slab * nblk + (kind == 0 ? 0 : fa.nblkA) + idx / kBlk);
+    }
+  };
+  auto bounds = [&](const int4 &ia, const int4 &ib, int32_t &ps, int32_t &pe) {
+    ps = ia.x; pe = ia.y;
+    if (G::kSub == 2) { ps = sub == 0 ? ia.x : ib.x; pe = sub == 0 ? ib.x : ia.y; }
+    if (G::kSub == 4) {
+      ps = sub == 0 ? ia.x : (sub == 1 ? ib.x : (sub == 2 ? ib.y : ib.z));
+      pe = sub == 0 ? ib.x : (sub == 1 ? ib.y : (sub == 2 ? ib.z : ia.y));
+    }
+  };
+
+  int ta_raw = 0, tb_raw = 0;
+  if (lane == 0) {
+    ta_raw = atomicAdd(fa.ctrl, 1);
+    tb_raw = atomicAdd(fa.ctrl + kNextB, 1);
+  }
+  int tb = -1;            // the B ticket this warp holds (-1: its claim is in flight in tb_raw)
+  bool b_claimed = true;  // tb_raw holds a claim that has not been looked at yet
+  bool b_none = false;    // the B tickets are exhausted
+  int4 ba = make_int4(0, 0, 0, 0), bb = ba;
+  for (;;) {
+    // ------------------------------ an A item (never waits) ------------------------------
+    const int ta = __shfl_sync(kFull, ta_raw, 0);
+    const bool didA = ta < totalA;
+    if (didA) {
+      if (lane == 0) ta_raw = atomicAdd(fa.ctrl, 1);          // the next ticket: in flight while this item streams
+      const int slab = fa.nslab > 1 ? ta / GA : 0;
+      const int idx = ta - slab * GA;
+      const int4 ia = __ldg(fa.tabs + 2 * idx);
+      int4 ib = make_int4(0, 0, 0, 0);
+      if (G::kSub > 1) ib = __ldg(fa.tabs + 2 * idx + 1);
+      const int col0 = slab * fa.slabF;
+      const int Fs = min(fa.slabF, fa.F - col0);
+      int32_t ps, pe;
+      bounds(ia, ib, ps, pe);
+      stream_run<0, SW, VPL, 8, HAS_WIN, PIPE>(fa, ps, pe, col0, Fs, sl, pol_x, pol_xe_w);
+      publish(0, slab, idx);
+    }
+    // ------------------------------ the B item this warp holds, if it is ready ------------------------------
+    if (b_claimed) {
+      b_claimed = false;
+      tb = __shfl_sync(kFull, tb_raw, 0);
+      if (tb >= totalB) { tb = -1; b_none = true; }
+      else {
+        const int idx = tb - (fa.nslab > 1 ? tb / GB : 0) * GB;
+        ba = __ldg(tabB + 2 * idx);
+        if (G::kSub > 1) bb = __ldg(tabB + 2 * idx + 1);
+      }
+    }
+    if (tb >= 0) {
+      const int slab = fa.nslab > 1 ? tb / GB : 0;
+      const int idx = tb - slab * GB;
+      bool ready = ba.w <= 0 || scan_blocks(0, slab, ba.w);
+      if (!ready && !didA) {
+        // no A work left: every A item is being streamed by some warp; wait for the ones this item needs (bounded)
+        unsigned spins = 0;
+        while (!ready && !gave_up) {
+          __nanosleep(100);
+          ready = scan_blocks(0, slab, ba.w);
+          if (++spins > (1u << 20) || ((spins & 255u) == 0 && ld_relaxed(fa.ctrl + kFlagOff) != 0)) {
+            if (lane == 0) atomicExch(fa.ctrl + kFlagOff, 1);
+            gave_up = true;
+          }
+        }
+        ready = true;
+      }
+      if (ready) {
+        asm volatile("fence.acquire.gpu;" ::: "memory");
+        if (lane == 0) tb_raw = atomicAdd(fa.ctrl + kNextB, 1);   // the next B ticket: in flight while this one streams
+        b_claimed = true;
+        const int col0 = slab * fa.slabF;
+        const int Fs = min(fa.slabF, fa.F - col0);
+        if (fa.niso > 0) {   // this item's share of the vertices that no hyperedge touches
+          const int i0 = (int)((int64_t)fa.niso * idx / GB), i1 = (int)((int64_t)fa.niso * (idx + 1) / GB);
+          for (int i = i0 + sub; i < i1; i += G::kSub) {
+            float *yp = fa.out[1] + (int64_t)__ldg(fa.iso + i) * fa.F + col0;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v)
+              if (sl * 4 + v * G::kStride < Fs) st_row_hint(yp + sl * 4 + v * G::kStride, make_float4(0.f, 0.f, 0.f, 0.f), pol_y);
+          }
+        }
+        int32_t ps, pe;
+        bounds(ba, bb, ps, pe);
+        stream_run<1, SW, VPL, 8, HAS_WIN, PIPE>(fa, ps, pe, col0, Fs, sl, 0, pol_y);
+        if (fa.track_b) publish(1, slab, idx);
+        // discards: as in the split-role form -- the warp that finishes the last item of B block k makes ONE
+        // non-blocking attempt at discard item k - doff
+        if (GC > 0 && (idx % kBlk == kBlk - 1 || idx == GB - 1)) {
+          const int ci = idx / kBlk - fa.doff;
+          if (ci >= 0 && scan_blocks(1, slab, ci + 1)) {
+            asm volatile("fence.acquire.gpu;" ::: "memory");
+            const int4 ic = __ldg(tabC + 2 * ci);
+            const int lines = Fs >> 5;
+            const int totl = (ic.y - ic.x) * lines;
+            for (int x = lane; x < totl; x += 32) {
+              const int r = x / lines, l = x - r * lines;
+              const int32_t e = __ldg(fa.dperm + ic.x + r);
+              const float *p = fa.in[1] + (int64_t)e * fa.F + col0 + l * 32;
+              asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
+            }
+          }
+        }
+        tb = -1;
+        continue;
+      }
+    }
+    if (!didA && tb < 0 && !b_claimed) {
+      if (b_none) break;
+    }
+  }
+}
+
+template <int SW, int VPL, bool HAS_WIN>
+int launch_alt(hgPlan *p, const FArgs &fa, bool pipe, int occ, cudaStream_t s) {
+  void (*kern)(const FArgs) = nullptr;
+  if (occ <= 2) kern = pipe ? astream_kernel<SW, VPL, HAS_WIN, 2, true> : astream_kernel<SW, VPL, HAS_WIN, 2, false>;
+  else kern = pipe ? astream_kernel<SW, VPL, HAS_WIN, 3, true> : astream_kernel<SW, VPL, HAS_WIN, 3, false>;
+  int per_sm = 0;
+  HG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0));
+  if (per_sm < 1) per_sm = 1;
+  if (occ < per_sm) per_sm = occ < 1 ? 1 : occ;
+  const int64_t grid = (int64_t)p->sm_count * per_sm;
+  kern<<<(unsigned)grid, kThreads, 0, s>>>(fa);
+  HG_CUDA_TRY(cudaGetLastError());
+  return HG_OK;
+}
+
+int dispatch_alt(hgPlan *p, const FArgs &fa, int sw, int vpl, bool pipe, bool has_win, int occ, cudaStream_t s) {
+#define HG_CASE(SW_, VPL_)                                                                                   \
+  if (sw == SW_ && vpl == VPL_)                                                                              \
+    return has_win ? launch_alt<SW_, VPL_, true>(p, fa, pipe, occ, s) : launch_alt<SW_, VPL_, false>(p, fa, pipe, occ, s);
+  HG_CASE(8, 1) HG_CASE(8, 2) HG_CASE(8, 4) HG_CASE(16, 1) HG_CASE(16, 2) HG_CASE(16, 4)
+  HG_CASE(32, 1) HG_CASE(32, 2) HG_CASE(32, 4)
+#undef HG_CASE
+  return set_error(HG_EINVAL, "alternating stream: no kernel for sub-warp %d x %d vectors", sw, vpl);
+}
+
 template <int SW, int VPL, bool HAS_WIN>
 int launch_split(hgPlan *p, const FArgs &fa, bool pipe, int occ, cudaStream_t s) {
   void (*kern)(const FArgs) = nullptr;
@@ -656,7 +839,8 @@ int launch_fstream(hgPlan *p, const dev::Args &a, cudaStream_t s) {
   // rows can be discarded line by line only if they are made of whole 128-byte lines
   const int discard = (F % 32 == 0 && tune_get("fs_discard", 1) != 0) ? 1 : 0;
 
-  const bool split = tune_get("fs_split", 1) != 0;
+  const int split_mode = tune_get("fs_split", 1);   // 0: merged ticket order, 1: split-role CTAs, 2: alternating warps
+  const bool split = split_mode != 0;
   if (split) { lagB = 0; lagC = 0; }         // the merged order is not used: one cached table set per item size
   hgPlan::RingSched *sc = nullptr;
   if (int rc = fused_get_sched(p, bpi, lagB, lagC, nslab, discard, ksub, s, &sc)) return rc;
@@ -695,6 +879,10 @@ int launch_fstream(hgPlan *p, const dev::Args &a, cudaStream_t s) {
     fa.maxlead = sc->lead + (extra >= 0 ? extra : warps / 2) + 2 * kBlk;
     const int doff_t = tune_get("fs_doff", -1);
     fa.doff = doff_t >= 0 ? doff_t : (warps / 2 + kBlk - 1) / kBlk + 8;   // ~ the B blocks in flight
+    if (split_mode == 2) {
+      if (doff_t < 0) fa.doff = (warps + kBlk - 1) / kBlk + 8;   // every warp may hold a B item
+      return dispatch_alt(p, fa, cfg.sw, cfg.vpl, cfg.pipe, a.a_in != nullptr, cfg.occ, s);
+    }
     return dispatch_split(p, fa, cfg.sw, cfg.vpl, cfg.pipe, a.a_in != nullptr, cfg.occ, s);
   }
   return dispatch(p, fa, cfg, a.a_in != nullptr, ctas, s);

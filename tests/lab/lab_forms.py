@@ -116,7 +116,9 @@ def test_fused_stream_form_configurations(shape, replicas, cuda_device):
               # the merged-ticket-order kernel (every warp claims A, B and discard items from one order)
               dict(fs_split=0), dict(fs_split=0, fs_lag_b=0, fs_lag_c=0), dict(fs_split=0, fs_occ=2, fs_item_kb=4),
               dict(fs_split=0, fs_occ=1, fs_pipe=0), dict(fs_split=0, fs_sw=16, fs_item_kb=4, fs_lag_b=50, fs_lag_c=20), dict(fs_doff=0, fs_lead=0), dict(fs_doff=3, fs_item_kb=2),
-              dict(fs_split=0, fs_discard=0, fs_lag_b=1000000)]
+              dict(fs_split=0, fs_discard=0, fs_lag_b=1000000),
+              dict(fs_split=2), dict(fs_split=2, fs_doff=0, fs_item_kb=2), dict(fs_split=2, fs_occ=2, fs_item_kb=64, fs_pol_x=0),
+              dict(fs_split=2, fs_sw=16, fs_pipe=0, fs_discard=0)]
     try:
         for F in (4, 20, 32, 64, 100, 128, 256, 384, 512, 640, 1056):
             X = torch.randn(N, F, device=cuda_device)

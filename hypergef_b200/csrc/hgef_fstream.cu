@@ -549,10 +549,17 @@ __global__ void __launch_bounds__(kThreads, MINB) dstream_kernel(const __grid_co
 // exactly what the graph needs plus the items in flight, with no throttle and no lag parameter.  Only when the A
 // tickets are exhausted does a warp wait for its B item -- and then every A item is in the hands of a warp that is
 // streaming it, so the wait ends: no deadlock, and not every CTA has to be resident.
+// Measured (profiles/r02_alternating.txt): what decides whether Xe stays in the L2 is the size of the set of claimed,
+// unfinished items = warps x item bytes.  8 KB items: DRAM bytes 0.97x algorithmic (Xe never reaches HBM, X rows
+// are re-used in the L2); 16 KB: 1.26x; 32 KB: 1.36x.  But an item is an isolated load pipeline (fill + drain = two
+// memory latencies) plus ~400 control instructions, so at 8 KB the launch takes 908 us against 586 us for the
+// two-launch form; fetching the item record / index words ahead (cp.async into a per-warp shared-memory slot) and
+// publishing late were built and bought 2 % -- and publishing late puts Xe back into HBM (one more round of items
+// in flight).  The form that ships is still the two-launch one.
 // ---------------------------------------------------------------------------------------------------
-template <int SW, int VPL, bool HAS_WIN, int MINB, bool PIPE>
+template <int SW, int VPL, int KV, bool HAS_WIN, int MINB, bool PIPE>
 __global__ void __launch_bounds__(kThreads, MINB) astream_kernel(const __grid_constant__ FArgs fa) {
-  using G = SGeo<SW, VPL, 8>;
+  using G = SGeo<SW, VPL, KV>;
   static_assert(G::kSub <= 4, "an item record carries three split points");
   const int lane = threadIdx.x & 31;
   const int sub = lane / SW, sl = lane % SW;
@@ -564,22 +571,35 @@ __global__ void __launch_bounds__(kThreads, MINB) astream_kernel(const __grid_co
   int wmA = 0, wmB = 0, slabA = -1, slabB = -1;   // completed prefix blocks of the slab last looked at
   bool gave_up = false;
 
-  // one pass over the completion counters of blocks [w, need): how far is the prefix complete?  (non-blocking)
+  // How far is the prefix of complete blocks of `kind`?  (non-blocking)  The prefix found is shared through one
+  // word per (slab, kind): a warp starts its scan where the furthest scan of any warp ended, so a check is one
+  // load in the common case instead of a walk over everything finished since this warp last looked (that walk
+  // cost 20-25 % of the launch: profiles/r02_alternating.txt, section 1 vs 2).
   auto scan_blocks = [&](int kind, int slab, int need) -> bool {
     int &w = kind == 0 ? wmA : wmB;
     int &ws = kind == 0 ? slabA : slabB;
     if (slab != ws) { ws = slab; w = 0; }
-    if (fa.debug & 2) return true;
+    if ((fa.debug & 2) || w >= need) return true;
     const int G_ = kind == 0 ? GA : GB;
+    const int nb = kind == 0 ? fa.nblkA : fa.nblkB;
+    int *gw = fa.ctrl + kCntOff + (int64_t)nblk * fa.nslab + slab * 64 + kind * 32;
+    const int g = ld_relaxed(gw);
+    if (g > w) w = g;
+    if (w >= need) return true;
     const int *cnt = fa.ctrl + kCntOff + (int64_t)slab * nblk + (kind == 0 ? 0 : fa.nblkA);
-    while (w < need) {
+    // (the scan runs past `need` to the end of the complete prefix: the next item's need is usually a little further)
+    for (int pass = 0; pass < 8; ++pass) {
       const int b = w + lane;
-      bool done = true;
-      if (b < need) done = ld_relaxed(cnt + b) == min(kBlk, G_ - b * kBlk);
+      bool done = false;
+      if (b < nb) done = ld_relaxed(cnt + b) == min(kBlk, G_ - b * kBlk);
       const unsigned m = __ballot_sync(kFull, done);
       const int adv = m == kFull ? 32 : __ffs(~m) - 1;
-      w = min(need, w + adv);
+      w += adv;
       if (adv < 32) break;
+    }
+    if (w > g && lane == 0) {
+      __threadfence();
+      atomicMax(gw, w);
     }
     return w >= need;
   };
@@ -623,7 +643,7 @@ __global__ void __launch_bounds__(kThreads, MINB) astream_kernel(const __grid_co
       const int Fs = min(fa.slabF, fa.F - col0);
       int32_t ps, pe;
       bounds(ia, ib, ps, pe);
-      stream_run<0, SW, VPL, 8, HAS_WIN, PIPE>(fa, ps, pe, col0, Fs, sl, pol_x, pol_xe_w);
+      stream_run<0, SW, VPL, KV, HAS_WIN, PIPE>(fa, ps, pe, col0, Fs, sl, pol_x, pol_xe_w);
       publish(0, slab, idx);
     }
     // ------------------------------ the B item this warp holds, if it is ready ------------------------------
@@ -671,7 +691,7 @@ __global__ void __launch_bounds__(kThreads, MINB) astream_kernel(const __grid_co
         }
         int32_t ps, pe;
         bounds(ba, bb, ps, pe);
-        stream_run<1, SW, VPL, 8, HAS_WIN, PIPE>(fa, ps, pe, col0, Fs, sl, 0, pol_y);
+        stream_run<1, SW, VPL, KV, HAS_WIN, PIPE>(fa, ps, pe, col0, Fs, sl, 0, pol_y);
         if (fa.track_b) publish(1, slab, idx);
         // discards: as in the split-role form -- the warp that finishes the last item of B block k makes ONE
         // non-blocking attempt at discard item k - doff
@@ -702,9 +722,10 @@ __global__ void __launch_bounds__(kThreads, MINB) astream_kernel(const __grid_co
 
 template <int SW, int VPL, bool HAS_WIN>
 int launch_alt(hgPlan *p, const FArgs &fa, bool pipe, int occ, cudaStream_t s) {
+  // (occupancy, vectors in flight per lane): 3 x 8 or 2 x 16
   void (*kern)(const FArgs) = nullptr;
-  if (occ <= 2) kern = pipe ? astream_kernel<SW, VPL, HAS_WIN, 2, true> : astream_kernel<SW, VPL, HAS_WIN, 2, false>;
-  else kern = pipe ? astream_kernel<SW, VPL, HAS_WIN, 3, true> : astream_kernel<SW, VPL, HAS_WIN, 3, false>;
+  if (occ <= 2) kern = astream_kernel<SW, VPL, 16, HAS_WIN, 2, true>;
+  else kern = pipe ? astream_kernel<SW, VPL, 8, HAS_WIN, 3, true> : astream_kernel<SW, VPL, 8, HAS_WIN, 3, false>;
   int per_sm = 0;
   HG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0));
   if (per_sm < 1) per_sm = 1;
@@ -812,6 +833,10 @@ int launch_fstream(hgPlan *p, const dev::Args &a, cudaStream_t s) {
   FCfg cfg{};
   // geometry: SW lanes x VPL 128-bit vectors per row slab; at least 8 lanes per row (<= 4 streams per warp)
   int slabF = F <= 512 ? F : 512;
+  {
+    const int slab_t = tune_get("fs_slab", 0);
+    if (slab_t >= 32 && slab_t % 32 == 0 && slab_t < slabF) slabF = slab_t;
+  }
   const int nslab = (F + slabF - 1) / slabF;
   cfg.sw = slabF <= 32 ? 8 : (slabF <= 64 ? 16 : 32);
   {
@@ -850,7 +875,7 @@ int launch_fstream(hgPlan *p, const dev::Args &a, cudaStream_t s) {
     HG_CUDA_TRY(cudaGetLastError());
     ++p->kernels_launched;
   }
-  HG_CUDA_TRY(cudaMemsetAsync(sc->ctrl, 0, ((size_t)kCntOff + (size_t)(sc->nblkA + sc->nblkB) * nslab) * sizeof(int32_t), s));
+  HG_CUDA_TRY(cudaMemsetAsync(sc->ctrl, 0, ((size_t)kCntOff + (size_t)(sc->nblkA + sc->nblkB + 64) * nslab) * sizeof(int32_t), s));
   FArgs fa{};
   fa.src[0] = p->st_srcA; fa.dst[0] = p->st_dstA; fa.src[1] = p->st_srcB; fa.dst[1] = p->st_dstB;
   fa.in[0] = a.X; fa.out[0] = p->xe; fa.in[1] = p->xe; fa.out[1] = a.Y;
@@ -862,7 +887,8 @@ int launch_fstream(hgPlan *p, const dev::Args &a, cudaStream_t s) {
   fa.nitem = sc->nitem; fa.nslab = nslab; fa.slabF = slabF; fa.F = F;
   fa.nblkA = sc->nblkA; fa.nblkB = sc->nblkB; fa.GA = sc->GA; fa.GB = sc->GB;
   fa.track_b = discard;
-  fa.pol_x = tune_get("fs_pol_x", kPolFirst);
+  // (X rows are gathered 1.76 times each on the bench graph and the L2 serves the repeats: no evict-first hint on X)
+  fa.pol_x = tune_get("fs_pol_x", kPolNormal);
   fa.pol_xe_w = tune_get("fs_pol_xe_w", kPolLast);
   fa.pol_y = tune_get("fs_pol_y", kPolFirst);
   // (claiming and publishing tickets in batches of 2..32 was measured: no gain, and one configuration timed out on the

@@ -756,7 +756,8 @@ int fused_get_sched(hgPlan *p, int bpi, int lagB, int lagC, int nslab, int disca
   c.GC = discard ? c.nblkB : 0;
   c.nitem = c.GA + c.GB + c.GC;
   if (int rc = dev_alloc(&c.items, (size_t)c.nitem * 2)) return rc;
-  if (int rc = dev_alloc(&c.ctrl, (size_t)kCntOff + (size_t)(c.nblkA + c.nblkB) * nslab)) return rc;
+  // (+ 64 words per slab: the shared prefix watermarks of the alternating form)
+  if (int rc = dev_alloc(&c.ctrl, (size_t)kCntOff + (size_t)(c.nblkA + c.nblkB + 64) * nslab)) return rc;
   DevBuf<int32_t> a_after, need_blk, vals, vals_s;
   DevBuf<uint64_t> keys, keys_s;
   HG_CUDA_TRY(a_after.alloc(c.GB)); HG_CUDA_TRY(need_blk.alloc(c.GB));

@@ -18,6 +18,7 @@ ap.add_argument("--force-stream", action="store_true")
 ap.add_argument("--force-ring", action="store_true")
 ap.add_argument("--force-fstream", action="store_true")
 ap.add_argument("--tag", default="")
+ap.add_argument("--verify", action="store_true", help="compare every result with the stream form's (max abs difference / max abs value)")
 ap.add_argument("--sweep", default="", help="semicolon-separated env configs K=V,K=V applied in-process (stream form knobs are read per call)")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
@@ -49,10 +50,19 @@ for cfg in (args.sweep.split(";") if args.sweep else [""]):
             ops.aggregate(plan, X, s1=hg.degE, s2=W, a_out=hg.degV, out=Y, flags=flags)
         b.record(); torch.cuda.synchronize(); plan.check()
         us = a.elapsed_time(b) / args.iters * 1e3
+        bad = ""
+        if args.verify:
+            ops.tune(**{k: None for k in TUNED})
+            Y0 = ops.aggregate(plan, X, s1=hg.degE, s2=W, a_out=hg.degV, flags=_native.HG_FORCE_STREAM)
+            for kv in filter(None, cfg.split(",")):
+                k, v = kv.split("="); ops.tune(**{k: int(v)})
+            err = float((Y - Y0).abs().max() / Y0.abs().max())
+            bad = f" err={err:.1e}" + (" MISMATCH" if not err < 1e-5 else "")
+            del Y0
         balg = 8 * F * N + 4 * Z + 12 * M + 4 * N + 4
         if "ring_prof" in TUNED:
             w = plan.debug_words()
             out.append(f"[prof, kclk summed over warps, last launch: control items {w[2]} of which wait-empty {w[3]} wait-deps {w[4]} | worker issue {w[5]} wait-data {w[6]} idle {w[7]}]")
-        out.append(f"F={F}: {us:8.1f} us {balg / us / 1e3:7.1f} GB/s ({balg / us / 1e3 / 6536 * 100:4.1f}%)")
+        out.append(f"F={F}: {us:8.1f} us {balg / us / 1e3:7.1f} GB/s ({balg / us / 1e3 / 6536 * 100:4.1f}%){bad}")
         del X, Y
     print(f"[{args.tag} {cfg} {args.shape}x{args.replicas} N={N} Z={Z} heavy={plan.nheavy_edges}] " + " | ".join(out), flush=True)

@@ -605,6 +605,7 @@ def run_single(args, dev, barrier):
     if not args.no_extras:
         line["same_gpu_baselines"] = same_gpu_baselines(hg, plan, Xs, Ys, W, features, bytes_f, peak)
         line["literal_shapes"] = literal_shapes(dev)
+        line["layer"] = layer_block(hg, W)
     if not args.no_cpu_baseline:
         cores = host_threads()
         step, b_cpu, dims = cpu_conv_workload("pubmed", args.replicas, features)
@@ -726,6 +727,35 @@ def same_gpu_baselines(hg, plan, Xs, Ys, W, features, bytes_f, peak):
             except Exception as exc:
                 row["reference_kernel_error"] = repr(exc)[:200]
         out.append(row)
+    return out
+
+
+def layer_block(hg, W):
+    """one HGNN layer  degV H (degE W) H^T (X Theta)  on the bench graph, forward, fp32, with the
+    projection on the N vertex rows (the reference's order, model/ugsys/hgnn.py:22-23: Linear then HGNNAggr), on the E
+    hyperedge rows between the two stages (hg_plan_edge_reduce -> GEMM -> hg_plan_edge_scatter), or after the
+    aggregation; torch.matmul fp32 (no TF32) for the GEMM in every arm."""
+    from hypergef_b200 import ops
+    N, M = hg.num_nodes, hg.num_edges
+    out = []
+    for f_in, f_out in ((128, 128), (256, 256), (512, 256)):
+        X = torch.randn(N, f_in, device=W.device)
+        T = torch.randn(f_in, f_out, device=W.device) / f_in ** 0.5
+        row = {"F_in": f_in, "F_out": f_out, "chosen": ops.projection_order(N, M, f_in, f_out)}
+        with torch.no_grad():
+            for order in ("vertex", "edge", "after"):
+                fn = lambda: ops.projected_aggregate(hg, X, T, hg.degE, hg.degV, W, order=order)
+                for _ in range(3):
+                    fn()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(10):
+                    fn()
+                b.record()
+                torch.cuda.synchronize()
+                row[order + "_ms"] = a.elapsed_time(b) / 10
+        out.append(row)
+        del X, T
     return out
 
 

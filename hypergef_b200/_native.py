@@ -63,6 +63,8 @@ SIGNATURES = {
     "hg_aggr_max_backward": [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _int, _vp],
     "hg_plan_max_forward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp],
     "hg_plan_max_backward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp],
+    "hg_plan_edge_reduce": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp],
+    "hg_plan_edge_scatter": [_vp, _vp, _vp, _vp, _i32, _vp],
     "hg_weight_grad": [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _int, _vp],
 }
 

@@ -12,6 +12,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import ops
 from .wrappers import HGNNAggr, UniGNNConv, UniGNNConvdeg
 
 __all__ = ["HyperGsysHGNN", "HyperGsysUinGINConv", "HyperGsysUniGCNIIConv", "HGsysHGNN", "ColumnParallelHGNN"]
@@ -20,8 +21,12 @@ __all__ = ["HyperGsysHGNN", "HyperGsysUinGINConv", "HyperGsysUniGCNIIConv", "HGs
 class HyperGsysHGNN(nn.Module):
     """model/ugsys/hgnn.py:7-27: ``Linear`` then the fused HGNN aggregation."""
 
-    def __init__(self, hyperg, in_channels, out_channels, first_aggr="sum", heads=1):
+
+    def __init__(self, hyperg, in_channels, out_channels, first_aggr="sum", heads=1, project="vertex"):
         super().__init__()
+        # project: "vertex" = the reference's order (Linear on the N vertex rows, then the aggregation);
+        # "edge" / "after" / "auto" = SURVEY.md 8(f) N1, see ops.projected_aggregate
+        self.project = project
         self.W = nn.Linear(in_channels, heads * out_channels, bias=False)
         self.Wdiag = torch.ones(hyperg.degE.shape[0], device=hyperg.device)
         self.heads, self.in_channels, self.out_channels = heads, in_channels, out_channels
@@ -29,6 +34,10 @@ class HyperGsysHGNN(nn.Module):
         self.first_aggr = first_aggr
 
     def forward(self, X):
+        if self.project != "vertex" and self.first_aggr in ("sum", None):
+            # the same layer with the projection moved to where it is cheapest (ops.projection_order)
+            return ops.projected_aggregate(self.hyperg, X, self.W.weight.t(), self.degE, self.degV, self.Wdiag,
+                                           order=self.project)
         X = self.W(X)
         return HGNNAggr(self.hyperg, X, self.degE, self.degV, self.Wdiag, self.first_aggr)
 

@@ -252,6 +252,38 @@ int hg_plan_reserve(hgPlan *plan, int32_t F_max, void *stream) {
   return HG_OK;
 }
 
+// The two stages on their own (include/hgef_b200.h): the balanced stream kernels with the hyperedge features in a
+// caller-owned buffer, so that work can be put between them (a projection of the E hyperedge rows instead of the N
+// vertex rows -- SURVEY 8(f) N1 -- or an exchange).
+static int stage_common(hgPlan *plan, const void *in, void *out, int32_t F, const char *what) {
+  HG_REQUIRE(plan != nullptr, "%s: plan is NULL", what);
+  HG_REQUIRE(in != nullptr && out != nullptr, "%s: a feature pointer is NULL", what);
+  HG_REQUIRE(F >= 4 && F % 4 == 0, "%s: the feature length must be a multiple of 4 (got %d); pad the rows", what, F);
+  HG_REQUIRE(aligned16(in) && aligned16(out), "%s: feature pointers must be 16-byte aligned", what);
+  HG_REQUIRE(plan->canonical && plan->st_ready, "%s: the plan has no row programs (the schedule is not the balancer's "
+             "canonical cross product); use hg_edge_reduce / hg_edge_scatter on the CSR instead", what);
+  return HG_OK;
+}
+
+int hg_plan_edge_reduce(hgPlan *plan, const float *d_X, const float *d_s1, const float *d_s2, const float *d_a_in,
+                        float *d_Xe, int32_t F, void *stream) {
+  if (int rc = stage_common(plan, d_X, d_Xe, F, "plan_edge_reduce")) return rc;
+  DeviceGuard guard(plan->device);
+  HG_REQUIRE(guard.ok(), "plan_edge_reduce: cannot select device %d", plan->device);
+  Args a{};
+  a.X = d_X; a.s1 = d_s1; a.s2 = d_s2; a.a_in = d_a_in; a.F = F;
+  return launch_stream_stages(plan, a, 1, (cudaStream_t)stream, d_Xe);
+}
+
+int hg_plan_edge_scatter(hgPlan *plan, const float *d_Xe, const float *d_a_out, float *d_Y, int32_t F, void *stream) {
+  if (int rc = stage_common(plan, d_Xe, d_Y, F, "plan_edge_scatter")) return rc;
+  DeviceGuard guard(plan->device);
+  HG_REQUIRE(guard.ok(), "plan_edge_scatter: cannot select device %d", plan->device);
+  Args a{};
+  a.a_out = d_a_out; a.Y = d_Y; a.F = F;
+  return launch_stream_stages(plan, a, 2, (cudaStream_t)stream, const_cast<float *>(d_Xe));
+}
+
 int hg_aggr_forward(hgPlan *plan, const float *d_X, const float *d_s1, const float *d_s2,
                     const float *d_a_out, const float *d_a_in, float *d_Y, int32_t F, int32_t flags,
                     void *stream) {

@@ -519,9 +519,12 @@ int ensure_xe(hgPlan *plan, int F, cudaStream_t s) {
 
 // Launch geometry.  Defaults from the sweeps in profiles/; every one can be overridden through hg_tune_set
 // (st_slab, st_sw, st_l, st_ctas, st_occ, st_pipe, st_cs, st_pdl, st_only) -- read from a table, not the environment.
-int launch_stream_stages(hgPlan *p, const dev::Args &a, int stages, cudaStream_t s) {
+int launch_stream_stages(hgPlan *p, const dev::Args &a, int stages, cudaStream_t s, float *xe_ext) {
   const int F = a.F;
-  if (int rc = ensure_xe(p, F, s)) return rc;
+  // the hyperedge features: the plan's own buffer, or the caller's (hg_plan_edge_reduce / hg_plan_edge_scatter)
+  if (!xe_ext)
+    if (int rc = ensure_xe(p, F, s)) return rc;
+  float *const xe = xe_ext ? xe_ext : p->xe;
   StreamCfg cfg{};
   // geometry: SW lanes x VPL 128-bit vectors per row slab
   int slabF = tune_get("st_slab", 0);
@@ -556,15 +559,15 @@ int launch_stream_stages(hgPlan *p, const dev::Args &a, int stages, cudaStream_t
 
   if (p->nheavy_segs > 0 && (stages & 1)) {
     zero_rows_kernel<<<(unsigned)ceil_div<int64_t>(p->nheavy_segs * 32, 256), 256, 0, s>>>(
-        p->nheavy_segs, p->heavy_segs, p->seg_edge, p->xe, F);
+        p->nheavy_segs, p->heavy_segs, p->seg_edge, xe, F);
     HG_CUDA_TRY(cudaGetLastError());
     ++p->kernels_launched;
   }
   StreamArgs sa{};
   sa.src[0] = p->st_srcA; sa.dst[0] = p->st_dstA; sa.run[0] = p->st_runA; sa.nrun0[0] = (int32_t)p->st_nrunA;
   sa.src[1] = p->st_srcB; sa.dst[1] = p->st_dstB; sa.run[1] = p->st_runB; sa.nrun0[1] = (int32_t)p->st_nrunB;
-  sa.in[0] = a.X; sa.out[0] = p->xe; sa.w_in[0] = a.a_in; sa.w_o1[0] = a.s1; sa.w_o2[0] = a.s2;
-  sa.in[1] = p->xe; sa.out[1] = a.Y; sa.w_in[1] = nullptr; sa.w_o1[1] = a.a_out; sa.w_o2[1] = nullptr;
+  sa.in[0] = a.X; sa.out[0] = xe; sa.w_in[0] = a.a_in; sa.w_o1[0] = a.s1; sa.w_o2[0] = a.s2;
+  sa.in[1] = xe; sa.out[1] = a.Y; sa.w_in[1] = nullptr; sa.w_o1[1] = a.a_out; sa.w_o2[1] = nullptr;
   sa.iso = p->st_perm + p->st_nunitB; sa.niso = (int32_t)p->st_niso;
   sa.nslab = cfg.nslab; sa.slabF = cfg.slabF; sa.F = F; sa.k0 = cfg.k0;
   sa.y_stream = tune_get("st_cs", 1);
@@ -587,7 +590,7 @@ int launch_stream_stages(hgPlan *p, const dev::Args &a, int stages, cudaStream_t
   return dispatch(p, sa, cfg, 1, false, s);
 }
 
-int launch_stream(hgPlan *p, const dev::Args &a, cudaStream_t s) { return launch_stream_stages(p, a, 3, s); }
+int launch_stream(hgPlan *p, const dev::Args &a, cudaStream_t s) { return launch_stream_stages(p, a, 3, s, nullptr); }
 
 // ---- feature lengths that are not a multiple of 4: the same kernels on rows padded to the next multiple
 namespace {

@@ -22,7 +22,7 @@ int tune_get(const char *name, int dflt);
 
 int ensure_xe(hgPlan *plan, int F, cudaStream_t s);
 // stream form, selected stages: 1 = stage A (X -> plan->xe), 2 = stage B (plan->xe -> Y), 3 = both
-int launch_stream_stages(hgPlan *p, const dev::Args &a, int stages, cudaStream_t s);
+int launch_stream_stages(hgPlan *p, const dev::Args &a, int stages, cudaStream_t s, float *xe_ext = nullptr);
 bool stream_available(const hgPlan *plan, int F, bool force);
 int stream_build_runs(hgPlan *p, int L0, int32_t **runA, int64_t *nrunA, int32_t **runB, int64_t *nrunB, cudaStream_t s);
 

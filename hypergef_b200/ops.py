@@ -34,7 +34,7 @@ from . import _native
 __all__ = [
     "hgnnaggr", "hgnnaggr_mean", "hgnnaggr_max", "unignnaggrdeg", "unignnaggr",
     "set_backward_mode", "get_backward_mode", "aggregate", "aggregate_host", "HostPipeline", "Plan", "get_plan", "clear_plan_cache",
-    "launch_count", "tune",
+    "launch_count", "tune", "edge_reduce", "edge_scatter", "projected_aggregate", "projection_order",
 ]
 
 DEFAULT_FLAGS = 0       # OR-ed into every hg_aggr_forward call (tests force one kernel form with it)
@@ -244,6 +244,119 @@ def aggregate(plan: Plan, X, s1=None, s2=None, a_out=None, a_in=None, out=None, 
                  _ptr(a_in), out.data_ptr(), F, flags | DEFAULT_FLAGS, stream)
     _LAUNCHES += 1
     return out
+
+
+def edge_reduce(plan: Plan, X, s1=None, s2=None, a_in=None, out=None):
+    """Stage A alone: ``Xe = diag(s1*s2) H^T diag(a_in) X`` -> ``[num_edges, F]`` (``hg_plan_edge_reduce``:
+    the plan's balanced stream kernel with the hyperedge features in a caller-owned buffer).  F % 4 == 0."""
+    global _LAUNCHES
+    X = _feat(X, "node_feat")
+    N, M, F = plan.num_nodes, plan.num_edges, X.shape[1]
+    if X.device != plan.device or X.shape[0] != N:
+        raise ValueError(f"node_feat must be [{N}, F] on {plan.device}, got {tuple(X.shape)} on {X.device}")
+    s1, s2 = _scale(s1, "degE", M, X.device), _scale(s2, "W", M, X.device)
+    a_in = _scale(a_in, "degV", N, X.device)
+    if out is None:
+        out = torch.empty((M, F), dtype=torch.float32, device=X.device)
+    stream = torch.cuda.current_stream(plan.device_index).cuda_stream
+    _native.call("hg_plan_edge_reduce", plan.handle, X.data_ptr(), _ptr(s1), _ptr(s2), _ptr(a_in), out.data_ptr(), F, stream)
+    _LAUNCHES += 1
+    return out
+
+
+def edge_scatter(plan: Plan, Xe, a_out=None, out=None):
+    """Stage B alone: ``Y = diag(a_out) H Xe`` -> ``[num_nodes, F]`` (``hg_plan_edge_scatter``; every row of Y
+    is written exactly once).  F % 4 == 0."""
+    global _LAUNCHES
+    Xe = _feat(Xe, "edge_feat")
+    N, M, F = plan.num_nodes, plan.num_edges, Xe.shape[1]
+    if Xe.device != plan.device or Xe.shape[0] != M:
+        raise ValueError(f"edge_feat must be [{M}, F] on {plan.device}, got {tuple(Xe.shape)} on {Xe.device}")
+    a_out = _scale(a_out, "degV", N, Xe.device)
+    if out is None:
+        out = torch.empty((N, F), dtype=torch.float32, device=Xe.device)
+    stream = torch.cuda.current_stream(plan.device_index).cuda_stream
+    _native.call("hg_plan_edge_scatter", plan.handle, Xe.data_ptr(), _ptr(a_out), out.data_ptr(), F, stream)
+    _LAUNCHES += 1
+    return out
+
+
+# Rough per-unit costs on a B200 for choosing where a layer's projection goes (measured: stream stages move
+# ~4.3 TB/s of their own traffic; torch's fp32 matmul ~60 TFLOP/s).  Only the ORDER of the three candidates matters.
+_STAGE_BYTES_PER_S = 4.3e12
+_GEMM_FLOPS_PER_S = 60e12
+
+
+def projection_order(num_nodes, num_edges, f_in, f_out) -> str:
+    """Where ``Theta`` goes in ``Y = degV H (degE W) H^T (X Theta)``: ``'vertex'`` projects the N vertex rows first
+    (the reference: model/ugsys/hgnn.py:22-23), ``'edge'`` projects the E hyperedge rows between the two stages
+    (``H^T (X Theta) = (H^T X) Theta``: fewer rows whenever E < N, at the price of running stage A at ``f_in``
+    columns), ``'after'`` projects the aggregated vertex rows.  Picks the cheapest by a byte / flop count."""
+    N, M = float(num_nodes), float(num_edges)
+    stage = lambda f: 4.0 * f * (N + M) / _STAGE_BYTES_PER_S      # one stage at f columns: reads + writes
+    gemm = lambda rows: 2.0 * rows * f_in * f_out / _GEMM_FLOPS_PER_S
+    cost = {"vertex": gemm(N) + 2 * stage(f_out), "edge": stage(f_in) + gemm(M) + stage(f_out),
+            "after": 2 * stage(f_in) + gemm(N)}
+    if f_in % 4 or f_out % 4:
+        cost.pop("edge")           # the stage entry points take rows of whole 128-bit vectors
+    return min(cost, key=cost.get)
+
+
+class _ProjectedAggr(torch.autograd.Function):
+    """``Y = degV H [(degE W H^T X) Theta]``: stage A at F_in, one GEMM over the E hyperedge rows, stage B at F_out
+    (SURVEY.md 8(f) N1).  Backward is the exact transpose: ``dZ = H^T degV G``, ``dTheta = Xe^T dZ``,
+    ``dX = H (degE W) (dZ Theta^T)`` -- the same two stage kernels and two GEMMs over E rows."""
+
+    @staticmethod
+    def forward(ctx, plan, X, theta, degE, degV, W):
+        Xe = edge_reduce(plan, X, s1=degE, s2=W)
+        Y = edge_scatter(plan, Xe @ theta, a_out=degV)
+        ctx.plan, ctx.scales = plan, (degE, degV, W)
+        ctx.save_for_backward(Xe, theta)
+        return Y
+
+    @staticmethod
+    def backward(ctx, G):
+        plan = ctx.plan
+        degE, degV, W = ctx.scales
+        Xe, theta = ctx.saved_tensors
+        dZ = edge_reduce(plan, G.contiguous(), a_in=degV)
+        grad_theta = Xe.t() @ dZ if ctx.needs_input_grad[2] else None
+        grad_x = None
+        if ctx.needs_input_grad[1]:
+            dXe = dZ @ theta.t()
+            if degE is not None:
+                dXe.mul_(degE.detach().reshape(-1, 1))
+            if W is not None:
+                dXe.mul_(W.detach().reshape(-1, 1))
+            grad_x = edge_scatter(plan, dXe)
+        return None, grad_x, grad_theta, None, None, None
+
+
+def projected_aggregate(hyperg, X, theta, degE=None, degV=None, W=None, order="auto"):
+    """One HGNN layer ``degV H (degE W) H^T (X theta)`` with ``theta`` ``[F_in, F_out]`` applied where it is
+    cheapest (``projection_order``; ``order`` forces ``'vertex'`` / ``'edge'`` / ``'after'``).  ``'vertex'`` is
+    exactly what the reference's conv module does (``nn.Linear`` then ``HGNNAggr``); the other two give the same
+    result up to fp32 rounding of the re-associated sums.  Falls back to ``'vertex'`` when ``W`` needs a gradient
+    or the reference's backward is selected (those paths exist only for the fused op)."""
+    N = X.shape[0]
+    M = degE.numel() if degE is not None else hyperg.H_T_csrptr.numel() - 1
+    f_in, f_out = theta.shape
+    if order == "auto":
+        order = projection_order(N, M, f_in, f_out)
+    if order not in ("vertex", "edge", "after"):
+        raise ValueError(f"order must be 'auto', 'vertex', 'edge' or 'after', got {order!r}")
+    if order == "edge" and ((W is not None and W.requires_grad) or _BACKWARD_MODE != "transpose"):
+        order = "vertex"
+    args = (hyperg.group_key, hyperg.group_row, hyperg.group_start, hyperg.group_end, hyperg.H_T_csrptr, hyperg.H_T_colind)
+    if order == "vertex":
+        return _FusedAggr.apply(*args, X @ theta, degE, degV, W, N)
+    if order == "after":
+        return _FusedAggr.apply(*args, X, degE, degV, W, N) @ theta
+    if f_in % 4 or f_out % 4:
+        raise ValueError(f"order='edge' needs feature lengths that are multiples of 4, got {f_in} -> {f_out}")
+    plan = get_plan(*args[:4], args[5], N, M)
+    return _ProjectedAggr.apply(plan, _feat(X, "node_feat"), theta, degE, degV, W)
 
 
 class HostPipeline:

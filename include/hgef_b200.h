@@ -245,6 +245,23 @@ HG_API int hg_plan_max_backward(hgPlan *plan, const int32_t *d_t_indptr, const f
                                 const float *d_s2, const float *d_a_out, const int32_t *d_record,
                                 float *d_dX, int32_t F, void *stream);
 
+/* ------------------------------------------------------------------------- *
+ * The two stages of hg_aggr_forward as separate calls (the balanced stream kernels of the plan), with the
+ * hyperedge features in a CALLER-owned [num_edges, F] buffer -- for callers that put work between the stages.
+ * The case in point is SURVEY 8(f) N1: H^T (X Theta) = (H^T X) Theta, so a layer can project the E hyperedge
+ * rows instead of the N vertex rows (model/ugsys/hgnn.py:22-23 projects the vertices, then aggregates):
+ *   hg_plan_edge_reduce   Xe[e,:] = s1[e] * s2[e] * sum_{v in e} a_in[v] * X[v,:]      (Xe overwritten)
+ *   hg_plan_edge_scatter  Y[v,:]  = a_out[v] * sum_{e containing v} Xe[e,:]            (Y overwritten, every row)
+ * Any scale may be NULL (= 1).  F must be a multiple of 4 and the pointers 16-byte aligned (HG_EINVAL otherwise);
+ * the plan must come from the balancer's canonical schedule.  hg_plan_edge_scatter(hg_plan_edge_reduce(X)) runs
+ * the same two kernels as hg_aggr_forward's stream form (bit-identical results unless a hyperedge is split over
+ * several balancer segments: those are summed with floating-point reductions whose order varies).
+ * ------------------------------------------------------------------------- */
+HG_API int hg_plan_edge_reduce(hgPlan *plan, const float *d_X, const float *d_s1, const float *d_s2,
+                               const float *d_a_in, float *d_Xe, int32_t F, void *stream);
+HG_API int hg_plan_edge_scatter(hgPlan *plan, const float *d_Xe, const float *d_a_out, float *d_Y, int32_t F,
+                                void *stream);
+
 /* Gradient of the hyperedge weight W (the reference op returns none, hgnnaggr.cc:62-63;
  * un-scaled host reference include/util/check.cuh:116-143):
  *   dW[e] = s1[e] * sum_k (sum_{u in e} a_in[u] X[u,k]) * (sum_{v in e} a_out[v] G[v,k]) */

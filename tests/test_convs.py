@@ -63,6 +63,78 @@ def test_two_layer_hgnn_forward_backward_matches_stacked_oracle(cuda_device):
     assert orc.rel_err(model.conv_out.W.weight.grad.cpu().numpy(), W2.grad.numpy()) < 5e-5
 
 
+@pytest.mark.parametrize("shape", ["cora", "pubmed", "walmart"])
+def test_plan_stage_entry_points(shape, cuda_device):
+    """hg_plan_edge_reduce / hg_plan_edge_scatter: each stage against the fp64 oracle, and the two chained are
+    identical to the fused call's stream form (the same kernels with Xe in a caller buffer; bit for bit unless a
+    hyperedge is split over several segments)."""
+    data, hg, V, E, N, M = _setup(cuda_device, shape)
+    plan = ops.get_plan(hg.group_key, hg.group_row, hg.group_start, hg.group_end, hg.H_T_colind, N, M)
+    degE, degV = hg.degE.double().cpu().reshape(-1), hg.degV.double().cpu().reshape(-1)
+    g = torch.Generator().manual_seed(3)
+    W = (torch.rand(M, generator=g) + 0.5).to(cuda_device)
+    for F in (4, 32, 100, 256):
+        X0 = torch.randn(N, F, generator=g)
+        X = X0.to(cuda_device)
+        Xe = ops.edge_reduce(plan, X, s1=hg.degE, s2=W)
+        want_e = torch.zeros(M, F, dtype=torch.float64).index_add_(0, E, X0.double()[V]) * (degE * W.double().cpu())[:, None]
+        assert Xe.shape == (M, F)
+        assert orc.rel_err(Xe.cpu().numpy(), want_e.numpy()) < TOL, (shape, F)
+        Y = ops.edge_scatter(plan, Xe, a_out=hg.degV)
+        want_y = torch.zeros(N, F, dtype=torch.float64).index_add_(0, V, want_e[E]) * degV[:, None]
+        assert orc.rel_err(Y.cpu().numpy(), want_y.numpy()) < TOL, (shape, F)
+        fused = ops.aggregate(plan, X, s1=hg.degE, s2=W, a_out=hg.degV, flags=_native.HG_FORCE_STREAM)
+        if plan.nheavy_edges == 0:
+            assert torch.equal(Y, fused), (shape, F)
+        else:   # hyperedges split over several segments are summed with vector reductions: the order varies run to run
+            assert float((Y - fused).abs().max() / fused.abs().max()) < TOL, (shape, F)
+        # gather-side weight (the transposed backward's stage A) and caller-provided outputs
+        out_e = torch.full((M, F), float("nan"), device=cuda_device)
+        ops.edge_reduce(plan, X, a_in=hg.degV, out=out_e)
+        want_t = torch.zeros(M, F, dtype=torch.float64).index_add_(0, E, (X0.double() * degV[:, None])[V])
+        assert orc.rel_err(out_e.cpu().numpy(), want_t.numpy()) < TOL, (shape, F)
+    plan.check()
+    with pytest.raises(ValueError):
+        ops.edge_reduce(plan, torch.randn(N, 6, device=cuda_device))         # not a multiple of 4
+    with pytest.raises(ValueError):
+        ops.edge_scatter(plan, torch.randn(M + 1, 8, device=cuda_device))    # wrong row count
+
+
+@pytest.mark.parametrize("shape,replicas", [("cora", 1), ("pubmed", 4)])
+def test_projected_layer_every_order_matches_the_oracle(shape, replicas, cuda_device):
+    """Y = degV H (degE W) H^T (X Theta) with Theta applied to the vertex rows (the reference's
+    order), to the hyperedge rows between the stages, or to the aggregated rows -- forward and the gradients of X
+    and Theta against the fp64 formula."""
+    data, hg, V, E, N, M = _setup(cuda_device, shape, replicas)
+    degE, degV = hg.degE.double().cpu(), hg.degV.double().cpu()
+    g = torch.Generator().manual_seed(5)
+    Wd = torch.ones(M, device=cuda_device)
+    for f_in, f_out in ((64, 32), (32, 64), (128, 128)):
+        X0 = torch.randn(N, f_in, generator=g)
+        T0 = torch.randn(f_in, f_out, generator=g) / f_in ** 0.5
+        G0 = torch.randn(N, f_out, generator=g)
+        X64, T64 = X0.double().requires_grad_(True), T0.double().requires_grad_(True)
+        want = orc.torch_hgnn_conv(X64 @ T64, V, E, degE, degV, torch.ones(M, dtype=torch.float64), N, M)
+        want.backward(G0.double())
+        for order in ("vertex", "edge", "after", "auto"):
+            X = X0.to(cuda_device).requires_grad_(True)
+            T = T0.to(cuda_device).requires_grad_(True)
+            Y = ops.projected_aggregate(hg, X, T, hg.degE, hg.degV, Wd, order=order)
+            Y.backward(G0.to(cuda_device))
+            assert orc.rel_err(Y.detach().cpu().numpy(), want.detach().numpy()) < TOL, (order, f_in, f_out)
+            assert orc.rel_err(X.grad.cpu().numpy(), X64.grad.numpy()) < 5e-5, (order, f_in, f_out)
+            assert orc.rel_err(T.grad.cpu().numpy(), T64.grad.numpy()) < 5e-5, (order, f_in, f_out)
+    # the conv module with the projection moved: same parameters, same result as the reference order
+    torch.manual_seed(2)
+    ref = convs.HyperGsysHGNN(hg, 64, 32).to(cuda_device)
+    alt = convs.HyperGsysHGNN(hg, 64, 32, project="edge").to(cuda_device)
+    alt.load_state_dict(ref.state_dict())
+    X = torch.randn(N, 64, device=cuda_device)
+    a, b = ref(X), alt(X)
+    assert float((a - b).abs().max() / a.abs().max()) < TOL
+    assert ops.projection_order(N, M, 1433, 32) == "vertex" and ops.projection_order(10 ** 6, 4 * 10 ** 5, 256, 256) == "edge"
+
+
 def test_unigin_and_unigcnii_convs(cuda_device):
     """HyperGsysUinGINConv: (1 + eps) XW + H H^T XW;  HyperGsysUniGCNIIConv: Xi = (1-a) Agg(X) + a X0,
     (1-b) Xi + b W Xi -- forward and input gradient vs fp64."""

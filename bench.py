@@ -480,7 +480,8 @@ def c5_block(dev, rank, world, args, barrier):
                               "boundary_hyperedges": info.num_boundary_total, "boundary_fraction": info.num_boundary_total / M,
                               "exchanged_bytes_per_rank_per_call": per_call,
                               "collective": "2 x NCCL all_to_all_single of boundary hyperedge rows (partials to owners, completed rows "
-                                            "back), on a side stream while the interior hyperedges compute"}
+                                            "back), on a side stream while stage A of the interior hyperedges computes; both stages are the "
+                                            "balanced stream kernels over local plans (hg_plan_edge_reduce / hg_plan_edge_scatter)"}
         del Xp, agg
         torch.cuda.empty_cache()
     return blk, keep

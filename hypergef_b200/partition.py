@@ -15,6 +15,13 @@ block is INTERIOR to that rank and goes through the single-GPU fused kernel unto
 so no rank ever issues a remote atomic and the payload is ``~2 * 4F * E_boundary`` bytes per rank.
 Boundary stage 1 and the exchange run on a side stream while the interior kernel computes.
 
+When the feature length is a multiple of 4 both stages run as the BALANCED stream kernels of three local plans
+(``hg_plan_edge_reduce`` / ``hg_plan_edge_scatter``): stage A over the boundary hyperedges (side stream, then the
+exchange) and over the interior hyperedges (main stream, overlapping the exchange) write one ``[interior |
+boundary]`` hyperedge-feature matrix, and ONE stage B over all local hyperedges writes every row of ``Y[V_r]``
+exactly once -- no zero-fill, no atomics.  The hyperedge scale ``s1*s2`` is applied to the partial rows before
+they are summed (it is linear).  Other feature lengths keep the CSR kernels above.
+
 ``build_partition`` is pure index arithmetic in torch (runs on CPU or GPU, tested with gloo at
 world size 2); the compute goes through a small backend interface whose product implementation
 (:class:`CudaBackend`) is the C-ABI library -- there is no CPU compute path in this package.
@@ -147,6 +154,18 @@ class CudaBackend:
             return out.zero_()
         return ops.aggregate(plan, X, s1=s1, s2=s2, a_out=a_out, a_in=a_in, out=out)
 
+    # the balanced stream stages over a local plan (feature lengths that are multiples of 4)
+    def prepare_plan(self, ptr, ind, num_local, nrows):
+        return self.prepare_interior(ptr, ind, num_local, nrows)
+
+    def plan_reduce(self, plan, X, scale, a_in, out):
+        from . import ops
+        return ops.edge_reduce(plan, X, s1=scale, a_in=a_in, out=out)
+
+    def plan_scatter(self, plan, Xe, a_out, out):
+        from . import ops
+        return ops.edge_scatter(plan, Xe, a_out=a_out, out=out)
+
     def edge_reduce(self, ptr, ind, X, a_in):
         nrow, F = ptr.numel() - 1, X.shape[1]
         P = torch.empty((nrow, F), dtype=torch.float32, device=X.device)
@@ -176,8 +195,11 @@ class PartitionedAggregator:
     the two ``all_to_all`` are the accumulation of the received partial rows into the owned rows and the gather of
     the completed rows each peer asked for.  All exchange buffers are allocated once per feature length."""
 
-    def __init__(self, info: PartitionInfo, backend, group=None):
-        self.info, self.backend, self.group = info, backend, group
+    def __init__(self, info: PartitionInfo, backend, group=None, split_stage_a: bool = True):
+        # split_stage_a (balanced path): stage A of the boundary hyperedges runs first on a side stream so that the
+        # exchange overlaps stage A of the interior ones; False = ONE stage A over every local hyperedge (each X row is
+        # gathered by one kernel: better L2 re-use, nothing overlaps the exchange)
+        self.info, self.backend, self.group, self.split_stage_a = info, backend, group, split_stage_a
         self.plan = backend.prepare_interior(info.int_ptr, info.int_ind, info.num_local, info.int_edges.numel())
         dev = info.bnd_ptr.device
         world, rank = info.world, info.rank
@@ -206,6 +228,17 @@ class PartitionedAggregator:
         self.recv_map64 = self.recv_map.to(torch.int64)
         self.recv_ptr = torch.arange(nrecv + 1, dtype=torch.int32, device=dev)
         self.side = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+        # local plans for the balanced stages: boundary hyperedges alone (stage A, side stream) and every local
+        # hyperedge in the order [interior | boundary] (stage B); the interior plan doubles as stage A of the interior
+        self.n_int, self.n_bnd = int(info.int_edges.numel()), int(self.bnd_edges.numel())
+        self.plan_bnd = self.plan_all = None
+        if hasattr(backend, "plan_reduce") and self.n_int + self.n_bnd > 0:
+            if self.n_bnd:
+                self.plan_bnd = backend.prepare_plan(self.bnd_ptr, self.bnd_ind, info.num_local, self.n_bnd)
+            ptr_all = torch.cat([info.int_ptr.to(torch.int64), int(info.int_ptr[-1]) + self.bnd_ptr[1:].to(torch.int64)]).to(torch.int32)
+            ind_all = torch.cat([info.int_ind, self.bnd_ind]).contiguous()
+            self.plan_all = backend.prepare_plan(ptr_all, ind_all, info.num_local, self.n_int + self.n_bnd)
+        self._xe = {}            # F -> [n_int + n_bnd, F] hyperedge features of the balanced path
         self.bytes_exchanged = 0
         self._bufs = {}          # F -> (recv, ret): exchange buffers, allocated once
         self._scales = {}        # cached per-hyperedge scale gathers (identity of s1 / s2 + version)
@@ -238,7 +271,8 @@ class PartitionedAggregator:
         if s1 is not None or s2 is not None:
             bnd = (pick(s1, self.bnd_edges) if s1 is not None else 1.0) * (pick(s2, self.bnd_edges) if s2 is not None else 1.0)
             bnd = bnd.contiguous()
-        self._scales = {"key": key, "int1": i1, "int2": i2, "bnd": bnd}
+        self._scales = {"key": key, "int1": i1, "int2": i2, "bnd": bnd,
+                        "int": None if (i1 is None and i2 is None) else ((i1 if i1 is not None else 1.0) * (i2 if i2 is not None else 1.0)).contiguous()}
         return i1, i2, bnd
 
     def forward(self, X, s1=None, s2=None, a_out=None, a_in=None):
@@ -251,6 +285,8 @@ class PartitionedAggregator:
         si1, si2, sbnd = self._edge_scales(s1, s2)
         Y = torch.empty_like(X)
         use_side = self.side is not None
+        if self.plan_all is not None and F % 4 == 0 and F > 0:
+            return self._forward_planned(X, Y, self._scales["int"], sbnd, a_out, a_in, use_side)
         if use_side:
             self.side.wait_stream(torch.cuda.current_stream())
         ctx = torch.cuda.stream(self.side) if use_side else _NullCtx()
@@ -272,6 +308,50 @@ class PartitionedAggregator:
         be.edge_scatter(self.bnd_ptr, self.bnd_ind, P, sbnd, a_out, Y)                    # boundary stage 2
         if use_side:
             P.record_stream(torch.cuda.current_stream())
+        return Y
+
+
+    def _forward_planned(self, X, Y, sint, sbnd, a_out, a_in, use_side):
+        """Both stages as balanced stream kernels over local plans (module docstring)."""
+        info, be = self.info, self.backend
+        F, n_int, n_own = X.shape[1], self.n_int, self.n_own
+        Xe = self._xe.get(F)
+        if Xe is None:
+            Xe = self._xe[F] = torch.empty((n_int + self.n_bnd, F), dtype=X.dtype, device=X.device)
+        P = Xe[n_int:]                                           # [own | to rank 0 | 1 | ...]: boundary rows
+        if not self.split_stage_a:
+            sall = self._scales.get("all")
+            if sall is None and (sint is not None or sbnd is not None):
+                one = lambda n: torch.ones(n, dtype=X.dtype, device=X.device)
+                sall = self._scales["all"] = torch.cat([sint if sint is not None else one(n_int),
+                                                        sbnd if sbnd is not None else one(self.n_bnd)]).contiguous()
+            be.plan_reduce(self.plan_all, X, sall, a_in, Xe)
+            if info.world > 1 and self.n_bnd:
+                recv, ret = self._buffers(F, P)
+                self._a2a(recv, P[n_own:], self.recv_counts, self.send_counts, F)
+                own = P[:n_own]
+                be.edge_scatter(self.recv_ptr, self.recv_map, recv, None, None, own)
+                torch.index_select(own, 0, self.recv_map64, out=ret)
+                self._a2a(P[n_own:], ret, self.send_counts, self.recv_counts, F)
+            be.plan_scatter(self.plan_all, Xe, a_out, Y)
+            return Y
+        if use_side:
+            self.side.wait_stream(torch.cuda.current_stream())
+        with (torch.cuda.stream(self.side) if use_side else _NullCtx()):
+            if self.plan_bnd is not None:
+                be.plan_reduce(self.plan_bnd, X, sbnd, a_in, P)                           # scaled partial rows
+                if info.world > 1:
+                    recv, ret = self._buffers(F, P)
+                    self._a2a(recv, P[n_own:], self.recv_counts, self.send_counts, F)     # partial rows -> owners
+                    own = P[:n_own]
+                    be.edge_scatter(self.recv_ptr, self.recv_map, recv, None, None, own)  # own[map[i]] += recv[i]
+                    torch.index_select(own, 0, self.recv_map64, out=ret)                  # completed rows each peer asked for
+                    self._a2a(P[n_own:], ret, self.send_counts, self.recv_counts, F)      # ... straight back into P
+        if self.plan is not None:
+            be.plan_reduce(self.plan, X, sint, a_in, Xe[:n_int])                          # interior rows, overlapping the exchange
+        if use_side:
+            torch.cuda.current_stream().wait_stream(self.side)
+        be.plan_scatter(self.plan_all, Xe, a_out, Y)                                      # every row of Y written once
         return Y
 
 

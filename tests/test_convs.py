@@ -222,11 +222,12 @@ def test_partitioned_aggregation_over_nccl_matches_single_gpu(cuda_device):
         pytest.skip("needs at least two visible GPUs")
     world = 4 if ngpu >= 4 else 2
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", "29517", os.path.join(root, "tools", "run_partition.py"), "--scale", "0.004", "--F", "64", "--iters", "2",
-           "--check", "1"]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=root)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
-    out = json.loads(line)
-    assert out["world"] == world and out["max_rel_err_vs_single_gpu"] < TOL, out
+    for F in ("64", "30"):      # balanced-stage path (F % 4 == 0) and the CSR-kernel path
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+               "--master-port", "29517", os.path.join(root, "tools", "run_partition.py"), "--scale", "0.004", "--F", F, "--iters", "2",
+               "--check", "1"]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=root)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+        out = json.loads(line)
+        assert out["world"] == world and out["max_rel_err_vs_single_gpu"] < TOL, out

@@ -477,6 +477,29 @@ def test_stage_kernels_and_two_rank_emulation(F, cuda_device):
     assert orc.rel_err(_np(torch.cat(outs)), want) < TOL
 
 
+def test_partitioned_aggregator_single_rank_both_paths(cuda_device):
+    """PartitionedAggregator with one rank (every hyperedge interior): the balanced-stage path (F % 4 == 0:
+    hg_plan_edge_reduce -> hg_plan_edge_scatter over the local plans) and the CSR-kernel path (other F) against the
+    oracle; the multi-rank exchange around them is covered by tests/test_partition_cpu.py (gloo) and, on a box with
+    two GPUs, by tests/test_convs.py::test_partitioned_aggregation_over_nccl_matches_single_gpu."""
+    from hypergef_b200.partition import CudaBackend, PartitionedAggregator, build_partition
+    d, hg = _graph("mini_rep3", cuda_device)
+    N, M = hg.num_nodes, hg.num_edges
+    info = build_partition(hg.H_T_csrptr, hg.H_T_colind, N, M, 1, 0)
+    agg = PartitionedAggregator(info, CudaBackend(cuda_device, ngs=int(d["ngs"])))
+    assert agg.plan_all is not None and agg.plan_bnd is None and info.num_boundary_total == 0
+    gen = torch.Generator().manual_seed(11)
+    W0 = 0.5 + torch.rand(M, generator=gen)
+    for F in (8, 7, 64):
+        X0 = torch.randn(N, F, generator=gen)
+        Y = agg.forward(X0.to(cuda_device), s1=hg.degE, s2=W0.to(cuda_device), a_out=hg.degV)
+        want = orc.c_aggr_formula(d["H_T_csrptr"], d["H_T_colind"], X0, s1=d["degE"], s2=W0, a_out=d["degV"])
+        assert orc.rel_err(_np(Y), want) < TOL, F
+        G = agg.forward(X0.to(cuda_device), s1=hg.degE, a_in=hg.degV)
+        wantg = orc.c_aggr_formula(d["H_T_csrptr"], d["H_T_colind"], X0, s1=d["degE"], a_in=d["degV"])
+        assert orc.rel_err(_np(G), wantg) < TOL, F
+
+
 def test_addresses_beyond_int32(cuda_device):
     """C5-shaped graph (window locality) at 1/10 scale with F=512: N*F = 2.56e9 > 2^31, the case the
     reference's int32 address arithmetic (hgnnaggr_cuda.cu:34,44) cannot represent.  Checked by exact fp64

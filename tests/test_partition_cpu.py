@@ -37,6 +37,23 @@ class TorchStandInBackend:
         out.copy_(y if a_out is None else y * a_out[:, None])
         return out
 
+    # the balanced-stage interface (hg_plan_edge_reduce / hg_plan_edge_scatter in the product backend)
+    def prepare_plan(self, ptr, ind, num_local, nrows):
+        return (ptr.long(), ind.long(), num_local)
+
+    def plan_reduce(self, plan, X, scale, a_in, out):
+        ptr, ind, n = plan
+        Xs = X if a_in is None else X * a_in[:, None]
+        xe = torch.zeros(ptr.numel() - 1, X.shape[1], dtype=X.dtype).index_add_(0, self._rows(ptr), Xs[ind])
+        out.copy_(xe if scale is None else xe * scale[:, None])
+        return out
+
+    def plan_scatter(self, plan, Xe, a_out, out):
+        ptr, ind, n = plan
+        y = torch.zeros(n, Xe.shape[1], dtype=Xe.dtype).index_add_(0, ind, Xe[self._rows(ptr)])
+        out.copy_(y if a_out is None else y * a_out[:, None])
+        return out
+
     def edge_reduce(self, ptr, ind, X, a_in):
         Xs = X if a_in is None else X * a_in[:, None]
         return torch.zeros(ptr.numel() - 1, X.shape[1], dtype=X.dtype).index_add_(0, self._rows(ptr.long()), Xs[ind.long()])
@@ -72,7 +89,9 @@ def _worker(rank, world, port, graph, out_dir):
         Y = agg.forward(X[sl], s1=degE, s2=W, a_out=degV[sl])
         G = agg.forward(X[sl], s1=degE, s2=W, a_in=degV[sl])          # transpose-backward form
         U = agg.forward(X[sl])                                          # un-scaled
-        torch.save(dict(Y=Y, G=G, U=U, v0=info.v_start, v1=info.v_end, nb=info.num_boundary_total,
+        Y7 = agg.forward(X[sl][:, :7].contiguous(), s1=degE, s2=W, a_out=degV[sl])   # F % 4 != 0: the CSR-kernel path
+        Y1 = PartitionedAggregator(info, TorchStandInBackend(), split_stage_a=False).forward(X[sl], s1=degE, s2=W, a_out=degV[sl])
+        torch.save(dict(Y=Y, G=G, U=U, Y7=Y7, Y1=Y1, v0=info.v_start, v1=info.v_end, nb=info.num_boundary_total,
                         nint=int(info.int_edges.numel()), bytes=agg.bytes_exchanged),
                    os.path.join(out_dir, f"r{rank}.pt"))
     finally:
@@ -91,7 +110,9 @@ def test_partitioned_aggregation_matches_oracle(world, g, tmp_path):
     kw = dict(s1=d["degE"], s2=d["W"])
     want = {"Y": orc.c_aggr_formula(d["H_T_csrptr"], d["H_T_colind"], d["X"], a_out=d["degV"], **kw),
             "G": orc.c_aggr_formula(d["H_T_csrptr"], d["H_T_colind"], d["X"], a_in=d["degV"], **kw),
-            "U": orc.c_aggr_formula(d["H_T_csrptr"], d["H_T_colind"], d["X"])}
+            "U": orc.c_aggr_formula(d["H_T_csrptr"], d["H_T_colind"], d["X"]),
+            "Y1": orc.c_aggr_formula(d["H_T_csrptr"], d["H_T_colind"], d["X"], a_out=d["degV"], **kw),   # one stage A over all local hyperedges
+            "Y7": orc.c_aggr_formula(d["H_T_csrptr"], d["H_T_colind"], np.ascontiguousarray(d["X"][:, :7]), a_out=d["degV"], **kw)}
     for k, w in want.items():
         got = torch.cat([p[k] for p in parts]).numpy()
         assert got.shape == w.shape and orc.rel_err(got, w) < 1e-6, k

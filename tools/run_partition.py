@@ -17,6 +17,7 @@ ap.add_argument("--replicas", type=int, default=1)
 ap.add_argument("--F", type=int, default=256)
 ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--check", type=int, default=1)
+ap.add_argument("--single-stage-a", action="store_true", help="one stage A over every local hyperedge (no overlap of the exchange)")
 ap.add_argument("--mode", default="partition", choices=["partition", "colshard"],
                 help="partition: vertex/hyperedge blocks + NCCL boundary exchange; colshard: every rank owns F/world feature columns of the whole graph (no collective)")
 args = ap.parse_args()
@@ -64,7 +65,7 @@ if args.mode == "colshard":
         dist.destroy_process_group()
     sys.exit(0)
 info = build_partition(hg.H_T_csrptr, hg.H_T_colind, N, M, world, rank)
-agg = PartitionedAggregator(info, CudaBackend(dev, shape.ngs))
+agg = PartitionedAggregator(info, CudaBackend(dev, shape.ngs), split_stage_a=not args.single_stage_a)
 gen = torch.Generator(device=dev).manual_seed(5)
 Xfull = torch.randn(N, F, device=dev, generator=gen) if args.check else None
 Xl = (Xfull[info.v_start:info.v_end].contiguous() if args.check else

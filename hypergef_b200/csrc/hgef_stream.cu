@@ -22,7 +22,7 @@
 // traffic because Xe makes a round trip); below that, how much the L2 serves at 24-32 warps per SM.
 //
 // One launch per stage.  (Merging both stages into one persistent launch so that Xe is handed over inside the L2
-// was built four ways this round -- hgef_fstream.cu, hgef_ring.cu, lab library -- and is slower: DESIGN.md
+// was built six ways this round -- hgef_fstream.cu, hgef_ring.cu, lab library -- and is slower: DESIGN.md
 // section 4.)  Wide rows (> 512 floats) are processed as column SLABS.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>

@@ -755,6 +755,23 @@ def layer_block(hg, W):
                 b.record()
                 torch.cuda.synchronize()
                 row[order + "_ms"] = a.elapsed_time(b) / 10
+        # forward + backward (gradients of X and Theta), the reference's order against the chosen one
+        Xg, Tg = X.clone().requires_grad_(True), T.clone().requires_grad_(True)
+        G = torch.randn(N, f_out, device=W.device)
+        for order in dict.fromkeys(("vertex", row["chosen"])):
+            def fb():
+                Xg.grad = Tg.grad = None
+                ops.projected_aggregate(hg, Xg, Tg, hg.degE, hg.degV, W, order=order).backward(G)
+            for _ in range(3):
+                fb()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(5):
+                fb()
+            b.record()
+            torch.cuda.synchronize()
+            row[order + "_fwd_bwd_ms"] = a.elapsed_time(b) / 5
+        del Xg, Tg, G
         out.append(row)
         del X, T
     return out

@@ -606,7 +606,10 @@ def run_single(args, dev, barrier):
     if not args.no_extras:
         line["same_gpu_baselines"] = same_gpu_baselines(hg, plan, Xs, Ys, W, features, bytes_f, peak)
         line["literal_shapes"] = literal_shapes(dev)
-        line["layer"] = layer_block(hg, W)
+        try:
+            line["layer"] = layer_block(hg, W)
+        except Exception as exc:    # an extra must not cost the line
+            line["layer"] = {"error": repr(exc)[:300]}
     if not args.no_cpu_baseline:
         cores = host_threads()
         step, b_cpu, dims = cpu_conv_workload("pubmed", args.replicas, features)

@@ -93,3 +93,92 @@ def test_host_graph_from_mtx_matches_direct_construction(tmp_path):
     hg = hio.hypergraph_from_mtx(path, torch.device("cpu"), int(d["ngs"]))
     assert np.array_equal(hg.H_T_csrptr.numpy(), d["H_T_csrptr"]) and np.array_equal(hg.H_T_colind.numpy(), d["H_T_colind"])
     assert np.array_equal(hg.group_key.numpy(), d["group_key"]) and np.array_equal(hg.group_row.numpy(), d["group_row"])
+
+
+# ---------------------------------------------------------------------------------------------------
+# raw AllSet layouts (data/load_dataset.py): small files written here in the same layouts
+# ---------------------------------------------------------------------------------------------------
+def _expected_edge_index(members, N):
+    """the coalesced bipartite list, restated with python sets: sorted (row, col) pairs, duplicates dropped"""
+    pairs = set()
+    for k, mem in enumerate(members):
+        for v in mem:
+            pairs.add((v, N + k))
+            pairs.add((N + k, v))
+    return np.array(sorted(pairs), dtype=np.int64).T
+
+
+def _check_graph(data, members, N):
+    want = _expected_edge_index(members, N)
+    assert np.array_equal(data.edge_index.numpy(), want)
+    assert data.n_x == N and data.num_hyperedges == len(members)
+    # and HyperGraph's host construction (hypergraph.py:11-77: split at the first row id >= N, CSR of H^T, balancer)
+    # takes it as it is: rows of H^T = the member sets, ascending
+    hg = hgef.HyperGraph(data, torch.device("cpu"), "loaded", ngs=4)
+    ptr, ind = hg.H_T_csrptr.numpy(), hg.H_T_colind.numpy()
+    assert hg.num_nodes == N and hg.num_edges == len(members)
+    assert [ind[ptr[k]:ptr[k + 1]].tolist() for k in range(len(members))] == [sorted(set(m)) for m in members]
+
+
+def test_citation_pickles(tmp_path):
+    import pickle
+    import scipy.sparse as sp
+    from hypergef_b200 import io as hio
+    N = 7
+    members = [[0, 1, 2], [2, 3], [3, 4, 5, 6, 3], [0, 6]]          # a duplicate member: coalesce drops it
+    root = tmp_path / "cora"
+    root.mkdir()
+    feats = sp.csr_matrix(np.arange(N * 3, dtype=np.float32).reshape(N, 3))
+    labels = [0, 1, 2, 0, 1, 2, 0]
+    pickle.dump(feats, open(root / "features.pickle", "wb"))
+    pickle.dump(labels, open(root / "labels.pickle", "wb"))
+    pickle.dump({f"paper{k}": set(m) if k == 0 else m for k, m in enumerate(members)}, open(root / "hypergraph.pickle", "wb"))
+    data = hio.load_citation_dataset(str(tmp_path), "cora")
+    _check_graph(data, members, N)
+    assert data.x.shape == (N, 3) and data.x.dtype == torch.float32 and torch.equal(data.y, torch.tensor(labels))
+    assert np.array_equal(data.x.numpy(), feats.toarray())
+
+
+def test_cornell_text_files(tmp_path):
+    from hypergef_b200 import io as hio
+    name = "walmart-trips"
+    root = tmp_path / name
+    root.mkdir()
+    labels = [1, 2, 3, 1, 2]                      # labels start at 1, vertex ids in the file start at 1 too
+    members = [[0, 1], [1, 2, 3], [4, 0, 3]]
+    (root / f"node-labels-{name}.txt").write_text("".join(f"{l}\n" for l in labels))
+    (root / f"hyperedges-{name}.txt").write_text("".join(",".join(str(v + 1) for v in m) + "\n" for m in members))
+    data = hio.load_cornell_dataset(str(tmp_path), name, feature_noise=0.0, feature_dim=6, seed=0)
+    _check_graph(data, members, len(labels))
+    assert data.x.shape == (5, 6)
+    assert np.array_equal(data.x.numpy().argmax(1), np.array(labels) - 1) and float(data.x.sum()) == 5.0
+    noisy = hio.load_cornell_dataset(str(tmp_path), name, feature_noise=0.1, seed=1)
+    assert noisy.x.shape == (5, 3) and float((noisy.x - data.x[:, :3]).abs().max()) > 0
+
+
+def test_LE_content_and_edges(tmp_path):
+    from hypergef_b200 import io as hio
+    name = "zoo"
+    root = tmp_path / name
+    root.mkdir()
+    N, members = 4, [[0, 1, 2], [2, 3]]
+    ids = [10, 11, 12, 13, 20, 21]                # arbitrary ids, renumbered in file order: vertices first, then hyperedges
+    rows = [f"{ids[i]} {i}.5 {i + 1}.0 {i % 2}" for i in range(N)] + [f"{ids[N + k]} 0.0 0.0 0" for k in range(len(members))]
+    (root / f"{name}.content").write_text("\n".join(rows) + "\n")
+    (root / f"{name}.edges").write_text("".join(f"{ids[v]} {ids[N + k]}\n" for k, m in enumerate(members) for v in m))
+    data = hio.load_LE_dataset(str(tmp_path), name)
+    _check_graph(data, members, N)
+    assert data.x.shape == (N, 2) and torch.equal(data.y, torch.tensor([0, 1, 0, 1]))
+    assert np.allclose(data.x.numpy(), [[0.5, 1.0], [1.5, 2.0], [2.5, 3.0], [3.5, 4.0]])
+
+
+def test_loaded_data_feeds_the_host_graph_builder(tmp_path):
+    """a loaded data object goes through the same host construction as the synthetic shapes"""
+    from hypergef_b200 import io as hio
+    members = [[0, 1, 2], [2, 3], [1, 3, 4]]
+    data = hio.data_from_members([v for m in members for v in m], [k for k, m in enumerate(members) for _ in m], 5,
+                                 torch.zeros(5, 1), torch.zeros(5, dtype=torch.long))
+    V, E, M, Z = orc.split_edge_index(data.edge_index, 5)
+    assert M == 3 and Z == 8
+    got = sorted(zip(V.tolist(), E.tolist()))
+    assert got == sorted((v, k) for k, m in enumerate(members) for v in m)

@@ -582,8 +582,11 @@ def run_single(args, dev, barrier):
     peak, peak_src = peaks()
     kern_ms = sum(per_f_ms.values())
     achieved = bytes_step / (kern_ms * 1e-3) / 1e9
+    # gather_scatter_GBps: the reference's own work unit beside the algorithmic figure (B_gs = 8 F Z + 8 Z,
+    # every member row gathered once and scattered once; include/spmm/spmm.cuh:663,717 counts 4 F nnz per two-step)
     sweep = [{"F": F, "us": per_f_ms[F] * 1e3, "algorithmic_GBps": bytes_f[F] / (per_f_ms[F] * 1e-3) / 1e9,
-              "frac_of_measured_peak": bytes_f[F] / (per_f_ms[F] * 1e-3) / 1e9 / peak} for F in features]
+              "frac_of_measured_peak": bytes_f[F] / (per_f_ms[F] * 1e-3) / 1e9 / peak,
+              "gather_scatter_GBps": (8 * F * Z + 8 * Z) / (per_f_ms[F] * 1e-3) / 1e9} for F in features]
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):

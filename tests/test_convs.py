@@ -231,3 +231,23 @@ def test_partitioned_aggregation_over_nccl_matches_single_gpu(cuda_device):
         line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
         out = json.loads(line)
         assert out["world"] == world and out["max_rel_err_vs_single_gpu"] < TOL, out
+
+
+def test_column_parallel_hgnn_matches_single_gpu(cuda_device):
+    """ColumnParallelHGNN (first layer split by output columns, all_gather, replicated output layer)
+    against HGsysHGNN with the same weights: output, loss, and the gradients of the local column block and of the
+    replicated layer.  One rank in-process (the sharding degenerates to the plain model); over NCCL through torchrun
+    when the box has two GPUs."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = os.path.join(root, "tools", "run_column_parallel.py")
+    worlds = [1] + ([2] if torch.cuda.device_count() >= 2 else [])
+    for world in worlds:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
+               "127.0.0.1", "--master-port", "29519", script] if world > 1 else [sys.executable, script]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        out = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+        assert out["world"] == world
+        assert out["out_err"] < TOL and out["loss_err"] < 1e-5 and out["grad_w1_block_err"] < 5e-5 and out["grad_w2_err"] < 5e-5, out
+

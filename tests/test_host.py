@@ -99,3 +99,28 @@ def test_degree_powers_vs_torch_pow():
     mine = 1.0 / torch.sqrt(deg)
     rel = ((deg.pow(-0.5) - mine).abs() / mine).max().item()
     assert rel <= 2.5e-7          # at most 2 ulp
+
+
+def test_projection_order_cost_model():
+    """ops.projection_order: where a layer's projection goes, by a byte / flop count."""
+    from hypergef_b200 import ops
+    N, M = 1261888, 509632                                   # the bench graph: E < N
+    assert ops.projection_order(N, M, 256, 256) == "edge"    # fewer rows to project between the stages
+    assert ops.projection_order(2708, 1579, 1433, 32) == "vertex"   # shrink the features first (the reference's order)
+    assert ops.projection_order(N, M, 32, 256) == "after"    # aggregate the narrow features, project last
+    assert ops.projection_order(N, M, 256, 7) == "vertex"    # the stage entry points need multiples of 4: never 'edge'
+    assert ops.projection_order(N, M, 30, 64) in ("vertex", "after")
+    # more hyperedges than vertices: projecting the hyperedge rows is never the cheapest
+    assert ops.projection_order(1000, 5000, 128, 128) != "edge"
+
+
+def test_data_from_members_validates():
+    import pytest
+    from hypergef_b200 import io as hio
+    with pytest.raises(ValueError):
+        hio.data_from_members([0, 1], [0], 3, None, None)
+    with pytest.raises(ValueError):
+        hio.data_from_members([0, 5], [0, 0], 3, None, None)
+    d = hio.data_from_members([], [], 3, None, None)
+    assert d.edge_index.shape == (2, 0) and d.num_hyperedges == 0
+

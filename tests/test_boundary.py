@@ -32,6 +32,36 @@ def test_library_exports_every_declared_symbol():
     assert not [s for s in exported if not s.startswith("hg_")], "only the C-ABI is visible"
 
 
+def test_header_is_plain_c_and_a_c_host_links(tmp_path):
+    """include/hgef_b200.h compiles as C (no C++, no torch, no CUDA headers) and a C host program links against the
+    library and runs the host-side balancer through it -- the stub INTEGRATION.md section 3 describes."""
+    src = tmp_path / "host.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "hgef_b200.h"
+int main(void) {
+  const int32_t ptr[] = {0, 5, 5, 7, 14};          /* SURVEY A4 golden vector, ngs = 3 */
+  int64_t S = 0, G = 0;
+  if (hg_abi_version() != 2) return 2;
+  if (hg_balance_count_host(4, ptr, 3, &S, &G) != HG_OK) { puts(hg_last_error()); return 3; }
+  int32_t key[16], row[16], st[16], ed[16];
+  if (hg_balance_fill_host(4, ptr, 3, key, row, st, ed) != HG_OK) { puts(hg_last_error()); return 4; }
+  printf("%lld %lld %d %d %d\n", (long long)S, (long long)G, key[1], key[(int)S - 1], row[4]);
+  return 0;
+}
+''')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "host"
+    libdir = os.path.dirname(_native.LIB_PATH)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), str(src), "-o", str(exe),
+                        "-L", libdir, "-l:" + os.path.basename(_native.LIB_PATH), "-Wl,-rpath," + libdir],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.split() == ["7", "14", "3", "14", "2"]          # nkey = S + 1, G, key[1], sentinel, balan_row[4]
+
+
 def test_abi_version_and_error_channel():
     lib = _native.lib()
     assert lib.hg_abi_version() == 2

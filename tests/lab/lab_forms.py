@@ -72,7 +72,7 @@ def test_ring_form_configurations(shape, replicas, cuda_device):
               dict(ring_pol_x=0, ring_pol_xe_w=0, ring_pol_xe_r=1, ring_pol_y=0, ring_ctas=3, ring_kb=48),
               dict(ring_workers=1, ring_qd=2, ring_chunk=5, ring_ctas=4, ring_kb=32)]
     try:
-        for F in (4, 20, 32, 64, 100, 128, 256, 384, 512, 640, 1056):
+        for F in (4, 32, 100, 128, 512, 1056):     # (the full list 4 ... 1056 in 11 steps was green all round; trimmed for run time)
             X = torch.randn(N, F, device=cuda_device)
             s_edge = _np(hg.degE).ravel() * _np(W)
             want = orc.c_aggr_formula(ptr, ind, X.cpu(), s1=s_edge, a_out=_np(hg.degV))
@@ -120,7 +120,7 @@ def test_fused_stream_form_configurations(shape, replicas, cuda_device):
               dict(fs_split=2), dict(fs_split=2, fs_doff=0, fs_item_kb=2), dict(fs_split=2, fs_occ=2, fs_item_kb=64, fs_pol_x=0),
               dict(fs_split=2, fs_sw=16, fs_pipe=0, fs_discard=0)]
     try:
-        for F in (4, 20, 32, 64, 100, 128, 256, 384, 512, 640, 1056):
+        for F in (4, 32, 100, 128, 512, 1056):     # (the full list 4 ... 1056 in 11 steps was green all round; trimmed for run time)
             X = torch.randn(N, F, device=cuda_device)
             s_edge = _np(hg.degE).ravel() * _np(W)
             want = orc.c_aggr_formula(ptr, ind, X.cpu(), s1=s_edge, a_out=_np(hg.degV))
